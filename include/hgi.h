@@ -1,0 +1,185 @@
+/*
+ * hgi.h -- C ABI of libhgi_b200.so: the B200-native implementation of RustyHGI's
+ * hierarchical-grid encode/decode loop.
+ *
+ * This header is the drop-in boundary for that path.  The reference (Rust crate `hgi`) has no
+ * FFI of its own -- its public surface is the generic `Encoder<I,Q>` / `Decoder<I>` pair plus
+ * the `Quantizator`/`Interpolator` option types re-exported at src/lib.rs:16-23 -- so each entry
+ * point below cites the reference item it replaces (file:line relative to the reference tree).
+ * INTEGRATION.md shows the `extern "C"` block + safe wrappers a maintainer would add on the Rust
+ * side; include/hgi.hpp is the same mirror in C++.
+ *
+ * Conventions
+ *  - Planes are row-major u8 with stride == width, exactly `image::GrayImage` / `Grid::buffer`
+ *    (src/grid.rs:19-27).  A batch is `n_images` such planes back to back.
+ *  - Every function returns HGI_OK (0) or a negative hgi_status_t; nothing aborts or throws.
+ *  - `*_u8` entry points take HOST pointers (the reference-facing calls; copies are inside).
+ *    `*_dev` entry points take DEVICE pointers and enqueue on `stream` (a cudaStream_t passed as
+ *    void*; NULL = the context's own stream) without synchronising.
+ *  - A context is bound to one CUDA device; calls on one context are stream-ordered and must not
+ *    be issued concurrently from several host threads.  Distinct contexts are independent.
+ *  - There is no CPU fallback: if no CUDA device is usable, hgi_ctx_create fails.
+ */
+#ifndef HGI_H_
+#define HGI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGI_ABI_VERSION 1
+
+typedef struct hgi_ctx hgi_ctx_t;
+
+/* Status codes. */
+typedef enum {
+    HGI_OK = 0,
+    HGI_ERR_INVALID_ARG = -1,   /* null pointer, levels > HGI_MAX_LEVELS, bad enum, w*h overflow */
+    HGI_ERR_NO_DEVICE = -2,     /* no usable CUDA device / wrong architecture */
+    HGI_ERR_CUDA = -3,          /* a CUDA runtime call failed; see hgi_ctx_last_cuda_error */
+    HGI_ERR_ALLOC = -4,         /* host or device allocation failed */
+    HGI_ERR_BAD_MAGIC = -5,     /* archive: "incorrect magic number" (src/archive.rs:47-50) */
+    HGI_ERR_TRUNCATED = -6,     /* archive: short read / corrupt deflate stream */
+    HGI_ERR_BUFFER_TOO_SMALL = -7,
+    HGI_ERR_UNSUPPORTED = -8    /* e.g. interpolation tag with no reference semantics */
+} hgi_status_t;
+
+/* src/interpolator.rs:4-9 `InterpolationType` (values = bincode variant indices).  Only Crossed
+   has an implementation in the reference; Line/Previous are serialisation tags without
+   semantics (-> HGI_ERR_UNSUPPORTED).  LeftTop (src/interpolator.rs:15-28) has no tag. */
+typedef enum {
+    HGI_INTERP_CROSSED = 0,
+    HGI_INTERP_LINE = 1,
+    HGI_INTERP_PREVIOUS = 2,
+    HGI_INTERP_LEFTTOP = 3
+} hgi_interp_t;
+
+/* src/quantizator.rs:17 `NoOp`, :36 `Linear`. */
+typedef enum { HGI_QUANT_NOOP = 0, HGI_QUANT_LINEAR = 1 } hgi_quant_kind_t;
+
+/* src/quantizator.rs:3-8 `QuantizationLevel` (values = bincode variant indices). */
+typedef enum {
+    HGI_QLEVEL_LOSSLESS = 0,
+    HGI_QLEVEL_LOW = 1,
+    HGI_QLEVEL_MEDIUM = 2,
+    HGI_QLEVEL_HIGH = 3
+} hgi_quant_level_t;
+
+/* Which CUDA path a context uses.  Both produce identical bytes. */
+typedef enum {
+    HGI_PATH_TILE = 0,      /* default: fused multi-level shared-memory tile kernels */
+    HGI_PATH_PER_LEVEL = 1  /* one kernel per level over HBM (north_star's literal shape) */
+} hgi_path_t;
+
+#define HGI_MAX_LEVELS 31u
+
+/* Encoder/decoder options: `Encoder::new(interpolator, quantizator, scale_level)`
+   (src/encoder.rs:18-24) and `Decoder::new(interpolator)` + `levels` (src/decoder.rs:14-18). */
+typedef struct {
+    uint32_t levels;     /* scale_level; 0 => grid == image */
+    int32_t interp;      /* hgi_interp_t */
+    int32_t quant_kind;  /* hgi_quant_kind_t   (ignored by decode) */
+    int32_t quant_level; /* hgi_quant_level_t  (ignored by decode and by NoOp) */
+} hgi_params_t;
+
+/* ---- library / context ------------------------------------------------------------------ */
+int hgi_abi_version(void);
+const char *hgi_strerror(int status);
+
+/* Binds a context to CUDA device `device` (must be sm_100).  Holds the stream, scratch planes
+   and staging buffers, so steady-state calls do not allocate. */
+int hgi_ctx_create(int device, hgi_ctx_t **ctx_out);
+void hgi_ctx_destroy(hgi_ctx_t *ctx);
+int hgi_ctx_set_path(hgi_ctx_t *ctx, int path /* hgi_path_t */);
+int hgi_ctx_synchronize(hgi_ctx_t *ctx);
+/* cudaError_t of the last failing runtime call (0 if none) and its string. */
+int hgi_ctx_last_cuda_error(const hgi_ctx_t *ctx);
+const char *hgi_ctx_last_cuda_error_string(const hgi_ctx_t *ctx);
+/* Number of kernels this context has launched since creation (monotonic). */
+uint64_t hgi_ctx_kernel_launches(const hgi_ctx_t *ctx);
+
+/* ---- quantizator ------------------------------------------------------------------------ */
+/* `Linear::from(level)` / `NoOp::from(level)` (src/quantizator.rs:19-23,41-63): fills the
+   256-entry table `quantize(v) = table[v]` and `error()` (:71-73).  Pure host arithmetic. */
+int hgi_quant_table(int quant_kind, int quant_level, uint8_t table_out[256], uint8_t *error_out);
+
+/* ---- host-pointer entry points (reference-facing) -------------------------------------- */
+/* `Encoder::encode(&mut self, input: GrayImage) -> Grid` (src/encoder.rs:39-71).  `image` is not
+   modified (the reference consumes it by value and clobbers it, :64); `grid_out` receives
+   width*height residual bytes.  `recon_out` (nullable) receives the closed-loop reconstruction,
+   i.e. the final state of the reference's `input` == what Decoder::decode will return. */
+int hgi_encode_u8(hgi_ctx_t *ctx, const uint8_t *image, uint32_t width, uint32_t height,
+                  const hgi_params_t *params, uint8_t *grid_out, uint8_t *recon_out);
+
+/* `Decoder::decode(&mut self, (width,height), levels, &Grid) -> GrayImage`
+   (src/decoder.rs:18-46). */
+int hgi_decode_u8(hgi_ctx_t *ctx, const uint8_t *grid, uint32_t width, uint32_t height,
+                  const hgi_params_t *params, uint8_t *image_out);
+
+/* The same over `n_images` equally sized planes (one launch chain for the whole batch; copies
+   are chunked and overlapped with the kernels).  `hist_out` (nullable) receives one 256-bin
+   histogram of the residual bytes per image. */
+int hgi_encode_batch_u8(hgi_ctx_t *ctx, const uint8_t *images, uint32_t n_images, uint32_t width,
+                        uint32_t height, const hgi_params_t *params, uint8_t *grids_out,
+                        uint32_t *hist_out /* [n_images][256] or NULL */);
+int hgi_decode_batch_u8(hgi_ctx_t *ctx, const uint8_t *grids, uint32_t n_images, uint32_t width,
+                        uint32_t height, const hgi_params_t *params, uint8_t *images_out);
+
+/* Residual histogram / frequency table of `n` grid bytes (north_star's archive.rs stage; the
+   reference leaves this to flate2 behind src/archive.rs:36-38).  hist_out[v] = #{bytes == v}. */
+int hgi_histogram_u8(hgi_ctx_t *ctx, const uint8_t *grid, size_t n, uint64_t hist_out[256]);
+
+/* `hgi test` error metrics (src/main.rs:84-92,106): sum of squared differences, its integer
+   quotient by n (`sd /= uncompressed`), and the maximum absolute difference. */
+int hgi_error_metrics_u8(hgi_ctx_t *ctx, const uint8_t *before, const uint8_t *after, size_t n,
+                         uint64_t *sum_sq_out, uint64_t *sd_int_out, uint32_t *max_abs_out);
+
+/* ---- device-pointer entry points (the timed ones) -------------------------------------- */
+int hgi_encode_dev(hgi_ctx_t *ctx, const uint8_t *d_images, uint32_t n_images, uint32_t width,
+                   uint32_t height, const hgi_params_t *params, uint8_t *d_grids_out,
+                   uint8_t *d_recon_out /* nullable */,
+                   uint32_t *d_hist_out /* nullable; [n_images][256], overwritten */,
+                   void *stream);
+int hgi_decode_dev(hgi_ctx_t *ctx, const uint8_t *d_grids, uint32_t n_images, uint32_t width,
+                   uint32_t height, const hgi_params_t *params, uint8_t *d_images_out,
+                   void *stream);
+int hgi_histogram_dev(hgi_ctx_t *ctx, const uint8_t *d_grid, size_t n_per_image,
+                      uint32_t n_images, uint32_t *d_hist_out /* [n_images][256], overwritten */,
+                      void *stream);
+/* d_out[0] = sum of squares, d_out[1] = max abs (both u64, overwritten). */
+int hgi_error_metrics_dev(hgi_ctx_t *ctx, const uint8_t *d_before, const uint8_t *d_after,
+                          size_t n, uint64_t *d_out, void *stream);
+
+/* ---- archive container (src/archive.rs) -------------------------------------------------- */
+/* `Metadata` (src/archive.rs:15-22). */
+typedef struct {
+    uint32_t quantization_level; /* hgi_quant_level_t */
+    uint32_t interpolation;      /* hgi_interp_t tag (Crossed/Line/Previous) */
+    uint32_t width;
+    uint32_t height;
+    uint64_t scale_level;
+} hgi_metadata_t;
+
+#define HGI_ARCHIVE_MAGIC 0xBAADA555u /* src/archive.rs:13 */
+#define HGI_ARCHIVE_HEADER_BYTES 28u  /* magic + bincode(Metadata) */
+
+/* Upper bound of the serialised size for a grid of `n` bytes. */
+size_t hgi_archive_bound(size_t n);
+/* `Archive::serialize_to_writer` (src/archive.rs:31-41): MAGIC, bincode(metadata), then raw
+   DEFLATE (best compression) of bincode(Grid{buffer, width}).  `grid_width` is Grid::width
+   (src/grid.rs:4).  On success *out_len = bytes written. */
+int hgi_archive_serialize(const hgi_metadata_t *metadata, const uint8_t *grid, size_t grid_len,
+                          uint64_t grid_width, uint8_t *out, size_t out_capacity, size_t *out_len);
+/* `Archive::deserialize_from_reader` (src/archive.rs:43-55), split so the caller can allocate:
+   _header parses MAGIC + metadata (28 bytes); _grid inflates the payload into `grid_out`. */
+int hgi_archive_read_header(const uint8_t *data, size_t len, hgi_metadata_t *metadata_out);
+int hgi_archive_read_grid(const uint8_t *data, size_t len, uint8_t *grid_out, size_t grid_capacity,
+                          size_t *grid_len_out, uint64_t *grid_width_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGI_H_ */

@@ -1,0 +1,625 @@
+// hgi_capi.cu -- the C ABI of libhgi_b200.so (include/hgi.h): context, pass planning, host/device
+// entry points.  No CPU compute path exists here: every encode/decode/histogram goes through the
+// CUDA kernels, and context creation fails when there is no sm_100 device.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/hgi.h"
+#include "hgi_device.cuh"
+#include "hgi_kernels.h"
+
+namespace {
+
+constexpr int kSlots = 3;  // host-API pipeline depth (H2D / kernels / D2H overlap)
+constexpr size_t kChunkBytes = 64u << 20;
+
+struct DevBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    DevBuf in, out, aux;
+    uint32_t* hist = nullptr;
+    size_t hist_cap = 0;
+};
+
+}  // namespace
+
+struct hgi_ctx {
+    int device = 0;
+    int path = HGI_PATH_TILE;
+    cudaStream_t stream = nullptr;
+    cudaError_t last_err = cudaSuccess;
+    uint64_t launches = 0;
+    DevBuf compact[4];   // ping-pong {recon, q} compact planes of the coarse passes
+    DevBuf level_recon;  // per-level path: reconstruction planes when the caller gives none
+    Slot slots[kSlots];
+    unsigned long long* d_metrics = nullptr;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(hgi_ctx* ctx)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != ctx->device) {
+            cudaError_t e = cudaSetDevice(ctx->device);
+            if (e != cudaSuccess) { ctx->last_err = e; ok = false; }
+        }
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int fail(hgi_ctx* ctx, cudaError_t e)
+{
+    ctx->last_err = e;
+    (void)cudaGetLastError();  // clear the sticky-free error state
+    return e == cudaErrorMemoryAllocation ? HGI_ERR_ALLOC : HGI_ERR_CUDA;
+}
+
+#define HGI_CUDA(ctx, expr)                                  \
+    do {                                                     \
+        cudaError_t e__ = (expr);                            \
+        if (e__ != cudaSuccess) return fail((ctx), e__);     \
+    } while (0)
+
+int reserve(hgi_ctx* ctx, DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return HGI_OK;
+    if (b.p) {
+        HGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (auto& s : ctx->slots)
+            if (s.stream) HGI_CUDA(ctx, cudaStreamSynchronize(s.stream));
+        HGI_CUDA(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    const size_t want = (bytes + 255) & ~(size_t)255;
+    HGI_CUDA(ctx, cudaMalloc((void**)&b.p, want));
+    b.cap = want;
+    return HGI_OK;
+}
+
+int check_params(const hgi_params_t* p, bool encode)
+{
+    if (!p) return HGI_ERR_INVALID_ARG;
+    if (p->levels > HGI_MAX_LEVELS) return HGI_ERR_INVALID_ARG;
+    if (p->interp == HGI_INTERP_LINE || p->interp == HGI_INTERP_PREVIOUS) return HGI_ERR_UNSUPPORTED;
+    if (p->interp != HGI_INTERP_CROSSED && p->interp != HGI_INTERP_LEFTTOP) return HGI_ERR_INVALID_ARG;
+    if (encode) {
+        if (p->quant_kind != HGI_QUANT_NOOP && p->quant_kind != HGI_QUANT_LINEAR) return HGI_ERR_INVALID_ARG;
+        if (p->quant_kind == HGI_QUANT_LINEAR && (p->quant_level < 0 || p->quant_level > 3))
+            return HGI_ERR_INVALID_ARG;
+    }
+    return HGI_OK;
+}
+
+// Levels whose sub-step is >= max(w,h) have no new points (only (0,0) lies on their lattice and
+// it is a seed), so clamping `levels` leaves every byte unchanged.
+uint32_t effective_levels(uint32_t levels, uint32_t w, uint32_t h)
+{
+    const uint32_t m = w > h ? w : h;
+    uint32_t need = 0;
+    while (need < 32 && (1ull << need) < m) ++need;  // ceil(log2(m))
+    return levels < need ? levels : need;
+}
+
+struct Pass {
+    uint32_t d_log2, nlev;
+};
+
+// Split the hierarchy into passes of <= 4 levels, finest pass first in `out` order reversed later.
+std::vector<Pass> plan_passes(uint32_t levels)
+{
+    std::vector<Pass> fine_to_coarse;
+    uint32_t d = 0, rem = levels;
+    while (rem > 0) {
+        const uint32_t nl = rem < (uint32_t)hgi::kMaxPassLevels ? rem : (uint32_t)hgi::kMaxPassLevels;
+        fine_to_coarse.push_back({d, nl});
+        d += nl;
+        rem -= nl;
+    }
+    return std::vector<Pass>(fine_to_coarse.rbegin(), fine_to_coarse.rend());
+}
+
+inline uint32_t ceil_shift(uint32_t v, uint32_t sh)
+{
+    return (uint32_t)(((uint64_t)v + (1ull << sh) - 1) >> sh);
+}
+
+inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+// mode: hgi::kModeEncode / kModeDecode.  All pointers are device pointers.
+int run_tile_path(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images, uint32_t w, uint32_t h,
+                  uint32_t levels, const hgi_params_t* prm, uint8_t* grid_out, uint8_t* recon_out,
+                  uint32_t* hist, cudaStream_t st)
+{
+    const std::vector<Pass> passes = plan_passes(levels);
+    const uint32_t qerr = (mode == hgi::kModeEncode) ? hgi::level_error(prm->quant_kind, prm->quant_level) : 0u;
+    // compact planes: pass i (D>1) writes set (i&1), the next pass reads it
+    size_t max_compact = 0;
+    for (const Pass& ps : passes)
+        if (ps.d_log2 > 0) {
+            const size_t sz = (size_t)n_images * ceil_shift(w, ps.d_log2) * ceil_shift(h, ps.d_log2);
+            if (sz > max_compact) max_compact = sz;
+        }
+    if (max_compact) {
+        const int nbuf = passes.size() > 2 ? 4 : 2;
+        for (int i = 0; i < nbuf; ++i) {
+            if (mode == hgi::kModeDecode && (i & 1)) continue;  // decode carries no symbols
+            int rc = reserve(ctx, ctx->compact[i], max_compact);
+            if (rc) return rc;
+        }
+    }
+    const uint8_t* c_recon = nullptr;
+    const uint8_t* c_q = nullptr;
+    uint32_t cw = 0, ch = 0;
+    for (size_t i = 0; i < passes.size(); ++i) {
+        const Pass& ps = passes[i];
+        hgi::PassArgs a{};
+        a.src = src;
+        a.w = w;
+        a.h = h;
+        a.d_log2 = ps.d_log2;
+        a.nlev = ps.nlev;
+        a.wD = ceil_shift(w, ps.d_log2);
+        a.hD = ceil_shift(h, ps.d_log2);
+        a.cw = cw;
+        a.ch = ch;
+        a.c_recon = c_recon;
+        a.c_q = c_q;
+        a.tiles_x = (a.wD + hgi::kTileW - 1) / hgi::kTileW;
+        a.tiles_y = (a.hD + hgi::kTileH - 1) / hgi::kTileH;
+        a.n_images = n_images;
+        a.quant_error = qerr;
+        if (ps.d_log2 == 0) {
+            a.grid_out = grid_out;
+            a.recon_out = recon_out;
+            a.hist = hist;
+            a.vec_ok = (w % 16 == 0) && aligned16(src) && (grid_out == nullptr || aligned16(grid_out)) &&
+                       (recon_out == nullptr || aligned16(recon_out));
+        } else {
+            const int set = (int)(i & 1) * 2;
+            a.s_recon = ctx->compact[set].p;
+            a.s_q = ctx->compact[set + 1].p;
+        }
+        HGI_CUDA(ctx, hgi::launch_tile_pass(mode, prm->interp, a, st));
+        ctx->launches++;
+        c_recon = a.s_recon;
+        c_q = a.s_q;
+        cw = a.wD;
+        ch = a.hD;
+    }
+    return HGI_OK;
+}
+
+int run_level_path(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images, uint32_t w, uint32_t h,
+                   uint32_t levels, const hgi_params_t* prm, uint8_t* grid_out, uint8_t* recon_out,
+                   cudaStream_t st)
+{
+    const size_t plane = (size_t)w * h;
+    const uint32_t qerr = (mode == hgi::kModeEncode) ? hgi::level_error(prm->quant_kind, prm->quant_level) : 0u;
+    // images per sub-batch so that a private reconstruction scratch stays bounded
+    uint32_t per = n_images;
+    uint8_t* recon = recon_out;
+    if (mode == hgi::kModeEncode && recon == nullptr) {
+        const size_t budget = 1ull << 30;
+        per = (uint32_t)(budget / plane);
+        if (per < 1) per = 1;
+        if (per > n_images) per = n_images;
+        int rc = reserve(ctx, ctx->level_recon, (size_t)per * plane);
+        if (rc) return rc;
+        recon = ctx->level_recon.p;
+    }
+    for (uint32_t first = 0; first < n_images; first += per) {
+        const uint32_t cnt = (n_images - first < per) ? n_images - first : per;
+        const uint8_t* s = src + (size_t)first * plane;
+        uint8_t* r = (recon == recon_out) ? recon + (size_t)first * plane : recon;
+        uint8_t* g = grid_out ? grid_out + (size_t)first * plane : nullptr;
+        if (mode == hgi::kModeEncode) {
+            // `mut input: GrayImage` by value (src/encoder.rs:39): the reconstruction starts as the image
+            HGI_CUDA(ctx, cudaMemcpyAsync(r, s, (size_t)cnt * plane, cudaMemcpyDeviceToDevice, st));
+            HGI_CUDA(ctx, hgi::launch_seed(mode, s, g, w, h, levels, cnt, st));
+        } else {
+            // GrayImage::new is zero-filled (src/decoder.rs:19); every byte is overwritten below, but
+            // keep the reference's initial state so partial lattices can never leak stale data
+            HGI_CUDA(ctx, cudaMemsetAsync(r, 0, (size_t)cnt * plane, st));
+            HGI_CUDA(ctx, hgi::launch_seed(mode, s, r, w, h, levels, cnt, st));
+        }
+        ctx->launches++;
+        for (uint32_t level = 0; level < levels; ++level) {
+            hgi::LevelArgs a{};
+            a.grid_in = s;
+            a.grid_out = g;
+            a.recon = r;
+            a.w = w;
+            a.h = h;
+            a.step_log2 = levels - level;
+            a.n_images = cnt;
+            a.quant_error = qerr;
+            HGI_CUDA(ctx, hgi::launch_level(mode, prm->interp, a, st));
+            ctx->launches++;
+        }
+    }
+    return HGI_OK;
+}
+
+int run_dev(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images, uint32_t w, uint32_t h,
+            const hgi_params_t* prm, uint8_t* grid_out, uint8_t* recon_out, uint32_t* hist, cudaStream_t st)
+{
+    const size_t plane = (size_t)w * h;
+    if (n_images == 0 || plane == 0) return HGI_OK;
+    const uint32_t levels = effective_levels(prm->levels, w, h);
+    uint8_t* primary = (mode == hgi::kModeEncode) ? grid_out : recon_out;
+    bool hist_done = false;
+    if (hist) HGI_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)n_images * 256 * sizeof(uint32_t), st));
+    if (levels == 0) {
+        // L = 0: grid == image (src/encoder.rs:26-37 copies every pixel, the level loop is empty)
+        HGI_CUDA(ctx, cudaMemcpyAsync(primary, src, (size_t)n_images * plane, cudaMemcpyDeviceToDevice, st));
+        if (mode == hgi::kModeEncode && recon_out)
+            HGI_CUDA(ctx, cudaMemcpyAsync(recon_out, src, (size_t)n_images * plane, cudaMemcpyDeviceToDevice, st));
+    } else if (ctx->path == HGI_PATH_PER_LEVEL) {
+        int rc = run_level_path(ctx, mode, src, n_images, w, h, levels, prm, grid_out, recon_out, st);
+        if (rc) return rc;
+    } else {
+        int rc = run_tile_path(ctx, mode, src, n_images, w, h, levels, prm, grid_out, recon_out, hist, st);
+        if (rc) return rc;
+        hist_done = true;
+    }
+    if (hist && !hist_done) {
+        HGI_CUDA(ctx, hgi::launch_histogram(grid_out, plane, n_images, hist, st));
+        ctx->launches++;
+    }
+    return HGI_OK;
+}
+
+bool plane_size_ok(uint32_t w, uint32_t h, uint32_t n_images)
+{
+    const unsigned __int128 total = (unsigned __int128)w * h * n_images;
+    return total < ((unsigned __int128)1 << 62);
+}
+
+// Host-pointer batch driver: images are cut into chunks that flow through `kSlots` stream slots
+// (H2D -> kernels -> D2H), so copies in both directions overlap the kernels.
+int run_host(hgi_ctx* ctx, int mode, const uint8_t* in, uint32_t n_images, uint32_t w, uint32_t h,
+             const hgi_params_t* prm, uint8_t* out, uint8_t* recon_out, uint32_t* hist_out)
+{
+    const size_t plane = (size_t)w * h;
+    if (n_images == 0 || plane == 0) return HGI_OK;
+    uint32_t per = (uint32_t)(kChunkBytes / plane);
+    if (per < 1) per = 1;
+    if (per > n_images) per = n_images;
+    const uint32_t n_chunks = (n_images + per - 1) / per;
+    const int used = n_chunks < (uint32_t)kSlots ? (int)n_chunks : kSlots;
+    for (int s = 0; s < used; ++s) {
+        Slot& sl = ctx->slots[s];
+        if (!sl.stream) HGI_CUDA(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        int rc = reserve(ctx, sl.in, (size_t)per * plane);
+        if (!rc) rc = reserve(ctx, sl.out, (size_t)per * plane);
+        if (!rc && recon_out) rc = reserve(ctx, sl.aux, (size_t)per * plane);
+        if (rc) return rc;
+        if (hist_out && sl.hist_cap < (size_t)per * 256) {
+            if (sl.hist) HGI_CUDA(ctx, cudaFree(sl.hist));
+            sl.hist = nullptr;
+            sl.hist_cap = 0;
+            HGI_CUDA(ctx, cudaMalloc((void**)&sl.hist, (size_t)per * 256 * sizeof(uint32_t)));
+            sl.hist_cap = (size_t)per * 256;
+        }
+    }
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        Slot& sl = ctx->slots[c % kSlots];
+        const uint32_t first = c * per;
+        const uint32_t cnt = (n_images - first < per) ? n_images - first : per;
+        const size_t off = (size_t)first * plane, bytes = (size_t)cnt * plane;
+        // stream order on the slot protects its buffers from the previous chunk that used them
+        HGI_CUDA(ctx, cudaMemcpyAsync(sl.in.p, in + off, bytes, cudaMemcpyHostToDevice, sl.stream));
+        uint8_t* d_grid = (mode == hgi::kModeEncode) ? sl.out.p : nullptr;
+        uint8_t* d_recon = (mode == hgi::kModeEncode) ? (recon_out ? sl.aux.p : nullptr) : sl.out.p;
+        int rc = run_dev(ctx, mode, sl.in.p, cnt, w, h, prm, d_grid, d_recon, hist_out ? sl.hist : nullptr, sl.stream);
+        if (rc) return rc;
+        HGI_CUDA(ctx, cudaMemcpyAsync(out + off, sl.out.p, bytes, cudaMemcpyDeviceToHost, sl.stream));
+        if (mode == hgi::kModeEncode && recon_out)
+            HGI_CUDA(ctx, cudaMemcpyAsync(recon_out + off, sl.aux.p, bytes, cudaMemcpyDeviceToHost, sl.stream));
+        if (hist_out)
+            HGI_CUDA(ctx, cudaMemcpyAsync(hist_out + (size_t)first * 256, sl.hist, (size_t)cnt * 256 * sizeof(uint32_t),
+                                          cudaMemcpyDeviceToHost, sl.stream));
+    }
+    for (int s = 0; s < used; ++s) HGI_CUDA(ctx, cudaStreamSynchronize(ctx->slots[s].stream));
+    return HGI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hgi_abi_version(void) { return HGI_ABI_VERSION; }
+
+const char* hgi_strerror(int status)
+{
+    switch (status) {
+        case HGI_OK: return "ok";
+        case HGI_ERR_INVALID_ARG: return "invalid argument";
+        case HGI_ERR_NO_DEVICE: return "no usable CUDA device (sm_100 required; there is no CPU fallback)";
+        case HGI_ERR_CUDA: return "CUDA runtime error";
+        case HGI_ERR_ALLOC: return "allocation failed";
+        case HGI_ERR_BAD_MAGIC: return "incorrect magic number";
+        case HGI_ERR_TRUNCATED: return "truncated or corrupt archive";
+        case HGI_ERR_BUFFER_TOO_SMALL: return "output buffer too small";
+        case HGI_ERR_UNSUPPORTED: return "unsupported option (no reference semantics)";
+        default: return "unknown status";
+    }
+}
+
+int hgi_ctx_create(int device, hgi_ctx_t** ctx_out)
+{
+    if (!ctx_out) return HGI_ERR_INVALID_ARG;
+    *ctx_out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        (void)cudaGetLastError();
+        return HGI_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) return HGI_ERR_INVALID_ARG;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return HGI_ERR_NO_DEVICE;
+    if (prop.major != 10) return HGI_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+    hgi_ctx* ctx = new (std::nothrow) hgi_ctx();
+    if (!ctx) return HGI_ERR_ALLOC;
+    ctx->device = device;
+    DeviceGuard g(ctx);
+    cudaError_t e = g.ok ? cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) : ctx->last_err;
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_metrics, 2 * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        (void)cudaGetLastError();
+        return HGI_ERR_CUDA;
+    }
+    *ctx_out = ctx;
+    return HGI_OK;
+}
+
+void hgi_ctx_destroy(hgi_ctx_t* ctx)
+{
+    if (!ctx) return;
+    {
+        DeviceGuard g(ctx);
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        for (auto& b : ctx->compact) if (b.p) cudaFree(b.p);
+        if (ctx->level_recon.p) cudaFree(ctx->level_recon.p);
+        for (auto& s : ctx->slots) {
+            if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+            if (s.in.p) cudaFree(s.in.p);
+            if (s.out.p) cudaFree(s.out.p);
+            if (s.aux.p) cudaFree(s.aux.p);
+            if (s.hist) cudaFree(s.hist);
+        }
+        if (ctx->d_metrics) cudaFree(ctx->d_metrics);
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+int hgi_ctx_set_path(hgi_ctx_t* ctx, int path)
+{
+    if (!ctx || (path != HGI_PATH_TILE && path != HGI_PATH_PER_LEVEL)) return HGI_ERR_INVALID_ARG;
+    ctx->path = path;
+    return HGI_OK;
+}
+
+int hgi_ctx_synchronize(hgi_ctx_t* ctx)
+{
+    if (!ctx) return HGI_ERR_INVALID_ARG;
+    DeviceGuard g(ctx);
+    if (!g.ok) return HGI_ERR_CUDA;
+    HGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& s : ctx->slots)
+        if (s.stream) HGI_CUDA(ctx, cudaStreamSynchronize(s.stream));
+    return HGI_OK;
+}
+
+int hgi_ctx_last_cuda_error(const hgi_ctx_t* ctx) { return ctx ? (int)ctx->last_err : 0; }
+const char* hgi_ctx_last_cuda_error_string(const hgi_ctx_t* ctx)
+{
+    return ctx ? cudaGetErrorString(ctx->last_err) : "";
+}
+uint64_t hgi_ctx_kernel_launches(const hgi_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
+
+int hgi_quant_table(int quant_kind, int quant_level, uint8_t table_out[256], uint8_t* error_out)
+{
+    if (!table_out) return HGI_ERR_INVALID_ARG;
+    if (quant_kind != HGI_QUANT_NOOP && quant_kind != HGI_QUANT_LINEAR) return HGI_ERR_INVALID_ARG;
+    if (quant_kind == HGI_QUANT_LINEAR && (quant_level < 0 || quant_level > 3)) return HGI_ERR_INVALID_ARG;
+    const uint32_t e = hgi::level_error(quant_kind, quant_level);
+    for (uint32_t i = 0; i < 256; ++i) table_out[i] = (uint8_t)hgi::quant_entry(i, e);
+    if (error_out) *error_out = (uint8_t)e;
+    return HGI_OK;
+}
+
+int hgi_encode_dev(hgi_ctx_t* ctx, const uint8_t* d_images, uint32_t n_images, uint32_t width, uint32_t height,
+                   const hgi_params_t* params, uint8_t* d_grids_out, uint8_t* d_recon_out, uint32_t* d_hist_out,
+                   void* stream)
+{
+    if (!ctx) return HGI_ERR_INVALID_ARG;
+    int rc = check_params(params, true);
+    if (rc) return rc;
+    if (!plane_size_ok(width, height, n_images)) return HGI_ERR_INVALID_ARG;
+    if ((size_t)width * height * n_images == 0) return HGI_OK;
+    if (!d_images || !d_grids_out) return HGI_ERR_INVALID_ARG;
+    DeviceGuard g(ctx);
+    if (!g.ok) return HGI_ERR_CUDA;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    return run_dev(ctx, hgi::kModeEncode, d_images, n_images, width, height, params, d_grids_out, d_recon_out,
+                   d_hist_out, st);
+}
+
+int hgi_decode_dev(hgi_ctx_t* ctx, const uint8_t* d_grids, uint32_t n_images, uint32_t width, uint32_t height,
+                   const hgi_params_t* params, uint8_t* d_images_out, void* stream)
+{
+    if (!ctx) return HGI_ERR_INVALID_ARG;
+    int rc = check_params(params, false);
+    if (rc) return rc;
+    if (!plane_size_ok(width, height, n_images)) return HGI_ERR_INVALID_ARG;
+    if ((size_t)width * height * n_images == 0) return HGI_OK;
+    if (!d_grids || !d_images_out) return HGI_ERR_INVALID_ARG;
+    DeviceGuard g(ctx);
+    if (!g.ok) return HGI_ERR_CUDA;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    return run_dev(ctx, hgi::kModeDecode, d_grids, n_images, width, height, params, nullptr, d_images_out, nullptr, st);
+}
+
+int hgi_histogram_dev(hgi_ctx_t* ctx, const uint8_t* d_grid, size_t n_per_image, uint32_t n_images,
+                      uint32_t* d_hist_out, void* stream)
+{
+    if (!ctx || !d_hist_out) return HGI_ERR_INVALID_ARG;
+    if (n_per_image >= ((size_t)1 << 32)) return HGI_ERR_INVALID_ARG;  // u32 bins
+    if (n_images == 0) return HGI_OK;
+    if (!d_grid && n_per_image) return HGI_ERR_INVALID_ARG;
+    DeviceGuard g(ctx);
+    if (!g.ok) return HGI_ERR_CUDA;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    HGI_CUDA(ctx, hgi::launch_histogram(d_grid, n_per_image, n_images, d_hist_out, st));
+    ctx->launches++;
+    return HGI_OK;
+}
+
+int hgi_error_metrics_dev(hgi_ctx_t* ctx, const uint8_t* d_before, const uint8_t* d_after, size_t n,
+                          uint64_t* d_out, void* stream)
+{
+    if (!ctx || !d_out) return HGI_ERR_INVALID_ARG;
+    if (n && (!d_before || !d_after)) return HGI_ERR_INVALID_ARG;
+    DeviceGuard g(ctx);
+    if (!g.ok) return HGI_ERR_CUDA;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    HGI_CUDA(ctx, hgi::launch_error_metrics(d_before, d_after, n, (unsigned long long*)d_out, st));
+    if (n) ctx->launches++;
+    return HGI_OK;
+}
+
+int hgi_encode_batch_u8(hgi_ctx_t* ctx, const uint8_t* images, uint32_t n_images, uint32_t width, uint32_t height,
+                        const hgi_params_t* params, uint8_t* grids_out, uint32_t* hist_out)
+{
+    if (!ctx) return HGI_ERR_INVALID_ARG;
+    int rc = check_params(params, true);
+    if (rc) return rc;
+    if (!plane_size_ok(width, height, n_images)) return HGI_ERR_INVALID_ARG;
+    if ((size_t)width * height * n_images == 0) return HGI_OK;
+    if (!images || !grids_out) return HGI_ERR_INVALID_ARG;
+    DeviceGuard g(ctx);
+    if (!g.ok) return HGI_ERR_CUDA;
+    return run_host(ctx, hgi::kModeEncode, images, n_images, width, height, params, grids_out, nullptr, hist_out);
+}
+
+int hgi_decode_batch_u8(hgi_ctx_t* ctx, const uint8_t* grids, uint32_t n_images, uint32_t width, uint32_t height,
+                        const hgi_params_t* params, uint8_t* images_out)
+{
+    if (!ctx) return HGI_ERR_INVALID_ARG;
+    int rc = check_params(params, false);
+    if (rc) return rc;
+    if (!plane_size_ok(width, height, n_images)) return HGI_ERR_INVALID_ARG;
+    if ((size_t)width * height * n_images == 0) return HGI_OK;
+    if (!grids || !images_out) return HGI_ERR_INVALID_ARG;
+    DeviceGuard g(ctx);
+    if (!g.ok) return HGI_ERR_CUDA;
+    return run_host(ctx, hgi::kModeDecode, grids, n_images, width, height, params, images_out, nullptr, nullptr);
+}
+
+int hgi_encode_u8(hgi_ctx_t* ctx, const uint8_t* image, uint32_t width, uint32_t height, const hgi_params_t* params,
+                  uint8_t* grid_out, uint8_t* recon_out)
+{
+    if (!ctx) return HGI_ERR_INVALID_ARG;
+    int rc = check_params(params, true);
+    if (rc) return rc;
+    if (!plane_size_ok(width, height, 1)) return HGI_ERR_INVALID_ARG;
+    if ((size_t)width * height == 0) return HGI_OK;
+    if (!image || !grid_out) return HGI_ERR_INVALID_ARG;
+    DeviceGuard g(ctx);
+    if (!g.ok) return HGI_ERR_CUDA;
+    return run_host(ctx, hgi::kModeEncode, image, 1, width, height, params, grid_out, recon_out, nullptr);
+}
+
+int hgi_decode_u8(hgi_ctx_t* ctx, const uint8_t* grid, uint32_t width, uint32_t height, const hgi_params_t* params,
+                  uint8_t* image_out)
+{
+    return hgi_decode_batch_u8(ctx, grid, 1, width, height, params, image_out);
+}
+
+int hgi_histogram_u8(hgi_ctx_t* ctx, const uint8_t* grid, size_t n, uint64_t hist_out[256])
+{
+    if (!ctx || !hist_out) return HGI_ERR_INVALID_ARG;
+    for (int i = 0; i < 256; ++i) hist_out[i] = 0;
+    if (n == 0) return HGI_OK;
+    if (!grid) return HGI_ERR_INVALID_ARG;
+    DeviceGuard g(ctx);
+    if (!g.ok) return HGI_ERR_CUDA;
+    Slot& sl = ctx->slots[0];
+    if (!sl.stream) HGI_CUDA(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    const size_t chunk = (size_t)1 << 30;  // keeps the u32 device bins far from overflow
+    int rc = reserve(ctx, sl.in, n < chunk ? n : chunk);
+    if (rc) return rc;
+    if (sl.hist_cap < 256) {
+        if (sl.hist) HGI_CUDA(ctx, cudaFree(sl.hist));
+        sl.hist = nullptr;
+        sl.hist_cap = 0;
+        HGI_CUDA(ctx, cudaMalloc((void**)&sl.hist, 256 * sizeof(uint32_t)));
+        sl.hist_cap = 256;
+    }
+    uint32_t part[256];
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t len = (n - off < chunk) ? n - off : chunk;
+        HGI_CUDA(ctx, cudaMemcpyAsync(sl.in.p, grid + off, len, cudaMemcpyHostToDevice, sl.stream));
+        HGI_CUDA(ctx, hgi::launch_histogram(sl.in.p, len, 1, sl.hist, sl.stream));
+        ctx->launches++;
+        HGI_CUDA(ctx, cudaMemcpyAsync(part, sl.hist, sizeof(part), cudaMemcpyDeviceToHost, sl.stream));
+        HGI_CUDA(ctx, cudaStreamSynchronize(sl.stream));
+        for (int i = 0; i < 256; ++i) hist_out[i] += part[i];
+    }
+    return HGI_OK;
+}
+
+int hgi_error_metrics_u8(hgi_ctx_t* ctx, const uint8_t* before, const uint8_t* after, size_t n,
+                         uint64_t* sum_sq_out, uint64_t* sd_int_out, uint32_t* max_abs_out)
+{
+    if (!ctx) return HGI_ERR_INVALID_ARG;
+    if (n && (!before || !after)) return HGI_ERR_INVALID_ARG;
+    unsigned long long total = 0, mx = 0;
+    if (n) {
+        DeviceGuard g(ctx);
+        if (!g.ok) return HGI_ERR_CUDA;
+        Slot& sl = ctx->slots[0];
+        if (!sl.stream) HGI_CUDA(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        const size_t chunk = (size_t)256 << 20;
+        int rc = reserve(ctx, sl.in, n < chunk ? n : chunk);
+        if (!rc) rc = reserve(ctx, sl.out, n < chunk ? n : chunk);
+        if (rc) return rc;
+        for (size_t off = 0; off < n; off += chunk) {
+            const size_t len = (n - off < chunk) ? n - off : chunk;
+            unsigned long long part[2];
+            HGI_CUDA(ctx, cudaMemcpyAsync(sl.in.p, before + off, len, cudaMemcpyHostToDevice, sl.stream));
+            HGI_CUDA(ctx, cudaMemcpyAsync(sl.out.p, after + off, len, cudaMemcpyHostToDevice, sl.stream));
+            HGI_CUDA(ctx, hgi::launch_error_metrics(sl.in.p, sl.out.p, len, ctx->d_metrics, sl.stream));
+            ctx->launches++;
+            HGI_CUDA(ctx, cudaMemcpyAsync(part, ctx->d_metrics, sizeof(part), cudaMemcpyDeviceToHost, sl.stream));
+            HGI_CUDA(ctx, cudaStreamSynchronize(sl.stream));
+            total += part[0];
+            if (part[1] > mx) mx = part[1];
+        }
+    }
+    if (sum_sq_out) *sum_sq_out = total;
+    if (sd_int_out) *sd_int_out = n ? total / n : 0;  // src/main.rs:106 integer division
+    if (max_abs_out) *max_abs_out = (uint32_t)mx;
+    return HGI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+// hgi_kernels.h -- host-side launchers of the HGI CUDA kernels (internal to libhgi_b200.so).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace hgi {
+
+// ---- fused tile path ----------------------------------------------------------------------
+// One *pass* runs `nlev` (1..4) consecutive levels of the hierarchy for every tile of the
+// lattice {(x,y) : x,y multiples of D = 2^d_log2}; see DESIGN.md "Pass decomposition".
+constexpr int kTileW = 128;   // lattice points per tile row
+constexpr int kTileH = 64;    // lattice rows per tile
+constexpr int kTileThreads = 256;
+constexpr int kMaxPassLevels = 4;
+
+struct PassArgs {
+    const uint8_t* src;      // encode: image planes; decode: grid planes (full resolution)
+    uint8_t* grid_out;       // encode, D==1: grid planes
+    uint8_t* recon_out;      // D==1: encode: optional reconstruction planes; decode: image planes
+    const uint8_t* c_recon;  // compact reconstruction of the coarser pass (null => top pass)
+    const uint8_t* c_q;      // compact symbols of the coarser pass (encode, non-top)
+    uint8_t* s_recon;        // D>1: compact reconstruction written by this pass (wD x hD)
+    uint8_t* s_q;            // D>1, encode: compact symbols written by this pass
+    uint32_t* hist;          // D==1, encode, optional: [n_images][256] (pre-zeroed)
+    uint32_t w, h;           // full-resolution plane size
+    uint32_t wD, hD;         // lattice size of this pass: ceil(w/D), ceil(h/D)
+    uint32_t cw, ch;         // size of the coarser pass's compact planes
+    uint32_t d_log2;         // log2(D)
+    uint32_t nlev;           // levels fused in this pass (1..4); coarse step F = 2^nlev
+    uint32_t tiles_x, tiles_y;
+    uint32_t n_images;
+    uint32_t quant_error;    // 0 => identity quantizer
+    uint32_t vec_ok;         // D==1 and rows are 16-byte aligned => 128-bit global accesses
+};
+
+cudaError_t launch_tile_pass(int mode, int interp, const PassArgs& args, cudaStream_t stream);
+
+// ---- per-level path -----------------------------------------------------------------------
+struct LevelArgs {
+    const uint8_t* grid_in;  // decode: residual planes
+    uint8_t* grid_out;       // encode: residual planes
+    uint8_t* recon;          // reconstruction planes, updated in place (encode: starts as image)
+    uint32_t w, h;
+    uint32_t step_log2;      // coarse step of this level = 2^step_log2 (sub-step = step/2)
+    uint32_t n_images;
+    uint32_t quant_error;
+};
+cudaError_t launch_seed(int mode, const uint8_t* src, uint8_t* dst, uint32_t w, uint32_t h,
+                        uint32_t levels, uint32_t n_images, cudaStream_t stream);
+cudaError_t launch_level(int mode, int interp, const LevelArgs& args, cudaStream_t stream);
+
+// ---- reductions ---------------------------------------------------------------------------
+cudaError_t launch_histogram(const uint8_t* data, size_t n_per_image, uint32_t n_images,
+                             uint32_t* hist_out, cudaStream_t stream);
+cudaError_t launch_error_metrics(const uint8_t* before, const uint8_t* after, size_t n,
+                                 unsigned long long* out2, cudaStream_t stream);
+
+}  // namespace hgi

@@ -1,0 +1,136 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/hgi.h declares,
+and its host-only entry points (quantizer table, archive container, argument validation) behave
+like the reference.  No GPU compute is attempted here."""
+import ctypes
+import io
+import os
+import re
+import zlib
+
+import numpy as np
+import pytest
+
+import rustyhgi_b200 as hgi
+from conftest import ROOT, get_plane
+from oracle import c as oc
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "hgi.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hgi_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_functions()
+    assert len(names) >= 20
+    L = ctypes.CDLL(hgi.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/hgi.h but not exported"
+    assert sorted(hgi._lib.PROTOTYPES) == names
+
+
+def test_library_has_sm100a_kernels_only():
+    import subprocess
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", hgi.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_(\d+a?)", out.stdout))
+    assert archs == {"100a"}, archs
+
+
+@pytest.mark.parametrize("level,err", [(0, 0), (1, 10), (2, 20), (3, 30)])
+def test_quantizator_tables(level, err):
+    """Linear::from(level) (src/quantizator.rs:41-63): table and error()."""
+    lin = hgi.Linear.from_level(hgi.QuantizationLevel(level))
+    want, werr = oc.quant_table(oc.QUANT_LINEAR, level)
+    assert lin.error() == err == werr
+    assert (lin.table == want).all()
+    scale = 2 * err + 1
+    assert all(lin.quantize(v) == ((v + err) // scale * scale) & 255 for v in range(256))
+    noop = hgi.NoOp.from_level(hgi.QuantizationLevel(level))
+    assert noop.error() == 0 and (noop.table == np.arange(256)).all()
+
+
+def test_quantization_level_parsing():
+    assert hgi.QuantizationLevel.parse("medium") is hgi.QuantizationLevel.Medium
+    assert hgi.QuantizationLevel.parse("LOSSLESS") is hgi.QuantizationLevel.Lossless
+    with pytest.raises(ValueError):
+        hgi.QuantizationLevel.parse("loseless")       # README's spelling is not a variant
+
+
+def test_archive_header_and_payload_layout():
+    """8x8 Lossless L3 header bytes + bincode(Grid) payload, src/archive.rs:31-41."""
+    grid = oc.encode(get_plane("unit_8x8"), 3, qlevel=0)
+    md = hgi.Metadata(hgi.QuantizationLevel.Lossless, hgi.InterpolationType.Crossed, 8, 8, 3)
+    buf = io.BytesIO()
+    hgi.Archive(md, hgi.Grid(grid, 8)).serialize_to_writer(buf)
+    raw = buf.getvalue()
+    assert raw[:28].hex() == "55a5adba" "00000000" "00000000" "08000000" "08000000" "0300000000000000"
+    payload = zlib.decompress(raw[28:], -15)              # raw DEFLATE, no zlib header
+    assert payload == (64).to_bytes(8, "little") + grid.tobytes() + (8).to_bytes(8, "little")
+
+
+def test_archive_serde_roundtrip_like_reference_test():
+    """src/lib.rs:99-125 `serde`: serialize -> deserialize -> assert_eq."""
+    grid = oc.encode(get_plane("unit_8x8"), 3, qlevel=0)
+    archive = hgi.Archive(hgi.Metadata(0, 0, 8, 8, 3), hgi.Grid(grid, 8))
+    buf = io.BytesIO()
+    archive.serialize_to_writer(buf)
+    assert hgi.Archive.deserialize_from_reader(io.BytesIO(buf.getvalue())) == archive
+
+
+def test_archive_large_and_foreign_stream():
+    rng = np.random.default_rng(0)
+    grid = rng.integers(0, 7, 300_000).astype(np.uint8)
+    md = hgi.Metadata(2, 0, 600, 500, 4)
+    buf = io.BytesIO()
+    hgi.Archive(md, hgi.Grid(grid, 600)).serialize_to_writer(buf)
+    back = hgi.Archive.deserialize_from_reader(io.BytesIO(buf.getvalue()))
+    assert back.metadata == md and back.grid == hgi.Grid(grid, 600)
+    # a stream deflated by someone else (any conforming raw-DEFLATE encoder, e.g. flate2) is readable
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    foreign = buf.getvalue()[:28] + co.compress((grid.size).to_bytes(8, "little") + grid.tobytes() +
+                                                (600).to_bytes(8, "little")) + co.flush()
+    assert hgi.Archive.deserialize_from_reader(io.BytesIO(foreign)).grid == hgi.Grid(grid, 600)
+
+
+def test_archive_errors():
+    with pytest.raises(hgi.HgiError) as e:
+        hgi.Archive.deserialize_from_reader(io.BytesIO(b"\x00\x01\x02\x03" + bytes(40)))
+    assert e.value.status == -5 and "incorrect magic number" in str(e.value)   # src/archive.rs:47-50
+    good = io.BytesIO()
+    hgi.Archive(hgi.Metadata(0, 0, 4, 4, 1), hgi.Grid(np.arange(16, dtype=np.uint8), 4)).serialize_to_writer(good)
+    with pytest.raises(hgi.HgiError) as e:
+        hgi.Archive.deserialize_from_reader(io.BytesIO(good.getvalue()[:-3]))
+    assert e.value.status == -6
+    with pytest.raises(hgi.HgiError):
+        hgi.Archive.deserialize_from_reader(io.BytesIO(good.getvalue()[:10]))
+
+
+def test_no_cpu_fallback_and_argument_validation():
+    L = hgi.lib()
+    h = ctypes.c_void_p()
+    rc = L.hgi_ctx_create(0, ctypes.byref(h))
+    if rc == 0:
+        L.hgi_ctx_destroy(h)
+    else:
+        assert rc == -2 and b"no CPU fallback" in L.hgi_strerror(rc)    # fails loudly without a GPU
+    assert L.hgi_ctx_create(0, None) == -1
+    p = hgi._lib.Params(4, 0, 1, 2)
+    buf = np.zeros(16, np.uint8)
+    assert L.hgi_encode_u8(None, buf.ctypes.data, 4, 4, ctypes.byref(p), buf.ctypes.data, None) == -1
+    assert L.hgi_quant_table(7, 0, buf.ctypes.data, None) == -1
+    assert L.hgi_quant_table(1, 9, buf.ctypes.data, None) == -1
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the oracle (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "rustyhgi_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower(), os.path.join(dirpath, f)
+    for f in os.listdir(os.path.join(ROOT, "include")):
+        assert "hgi_oracle" not in open(os.path.join(ROOT, "include", f)).read()
