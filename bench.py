@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- encode+decode throughput of the HGI hot path on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[4], the largest single-GPU configuration; weak scaling): per GPU
+a batch of 4096 synthetic 1920x1080 8-bit frames, frame k = (x*y + 31k) & 255 (frame 0 is the
+reference's criterion bench image, benches/bench.rs:24-28), level = 4, interpolator Crossed,
+quantizator Linear at Lossless and at Medium.  One *step* = for q in (Lossless, Medium):
+Encoder::encode over the batch, then Decoder::decode over the batch.  `value` counts every pixel
+once per encode+decode round trip: Mpixel/s = n_gpus * 2 * frames * 1920*1080 / step_time.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Timed with CUDA events on the launching stream after W warm-up steps, barrier + synchronize on
+both sides, max over ranks.  The working set (8.5 GB per plane set) is far larger than the 126 MB
+L2, so no flush is needed between iterations.  `e2e` is the same metric through the host-pointer
+C-ABI calls (pinned host buffers, H2D + D2H inside the timed region).  `--impl reference` times
+the CPU restatement of the reference (oracle/, all host threads) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, LEVELS = 1920, 1080, 4
+QLEVELS = (0, 2)                      # Lossless, Medium
+FRAMES_PER_GPU = 4096
+METRIC = "encode+decode Mpixel/s"
+UNIT = "Mpixel/s"
+
+
+def workload_config(frames, n_gpus):
+    return {"workload": f"batch of {frames} synthetic 1080p frames per GPU, Lossless+Medium, level=4, Crossed "
+                        f"(BASELINE configs[4]; image-sharded, {n_gpus} GPU(s))",
+            "frames_per_gpu": frames, "width": W, "height": H, "levels": LEVELS,
+            "quantizators": ["Lossless", "Medium"], "interpolator": "Crossed", "parallelism": f"image-shard x{n_gpus}",
+            "l2_policy": "inputs (8.5 GB per plane set) >> 126 MB L2; no flush needed"}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def profiled_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0=0.0, t1=float("inf")):
+        """Summary of the samples that arrived in the host-time window [t0, t1]."""
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ts, r in self.rows:
+            if not (t0 <= ts <= t1 + 0.06):
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (its C restatement, oracle/ -- the
+    reference is nightly Rust and cannot be built here), all host threads, bounded sample."""
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import c as oc
+    threads = oc.max_threads()
+    sample = max(threads * 2, 32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    frames = np.stack([((xx * yy + 31 * k) & 255).astype(np.uint8) for k in range(sample)])
+
+    def step():
+        for q in QLEVELS:
+            grids = oc.encode_batch(frames, LEVELS, qlevel=q, n_threads=threads)
+            oc.decode_batch(grids, LEVELS, n_threads=threads)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = len(QLEVELS) * sample * W * H / dt / 1e6
+    desc = f"{sample} of the workload's 1080p frames per step, by-image pthreads"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(FRAMES_PER_GPU, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(budget_s=12.0):
+    import numpy as np
+    from oracle import c as oc
+    threads = oc.max_threads()
+    sample = max(threads * 2, 32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    frames = np.stack([((xx * yy + 31 * k) & 255).astype(np.uint8) for k in range(sample)])
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        for q in QLEVELS:
+            grids = oc.encode_batch(frames, LEVELS, qlevel=q, n_threads=threads)
+            oc.decode_batch(grids, LEVELS, n_threads=threads)
+        reps += 1
+        if time.perf_counter() - t0 > budget_s or reps >= 50:
+            break
+    dt = (time.perf_counter() - t0) / reps
+    # single-thread figure = the reference's own execution model (one image, one thread)
+    t1 = time.perf_counter()
+    g = oc.encode(frames[0], LEVELS, qlevel=2)
+    oc.decode(g, LEVELS)
+    st = time.perf_counter() - t1
+    return {"value": len(QLEVELS) * sample * W * H / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{sample} of the workload's 1080p frames x {reps} reps, by-image pthreads, oracle/hgi_oracle.c",
+            "single_thread_value": W * H / st / 1e6}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import rustyhgi_b200 as hgi
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    frames_n = args.frames
+    ctx = hgi.Context(local_rank)
+    encs = [hgi.Encoder(hgi.Crossed, hgi.Linear(hgi.QuantizationLevel(q)), LEVELS, ctx=ctx) for q in QLEVELS]
+    dec = hgi.Decoder(hgi.Crossed, ctx=ctx)
+
+    yy = torch.arange(H, device=dev, dtype=torch.int32)[:, None]
+    xx = torch.arange(W, device=dev, dtype=torch.int32)[None, :]
+    frames = torch.empty((frames_n, H, W), dtype=torch.uint8, device=dev)
+    first = rank * frames_n                                 # global frame index of this rank's shard
+    for k0 in range(0, frames_n, 256):
+        k = torch.arange(first + k0, first + min(k0 + 256, frames_n), device=dev, dtype=torch.int32)[:, None, None]
+        frames[k0:k0 + k.shape[0]] = ((xx * yy + 31 * k) & 255).to(torch.uint8)
+    grids = torch.empty_like(frames)
+    back = torch.empty_like(frames)
+    stream = torch.cuda.current_stream(dev)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    marks = []
+
+    def step(record):
+        row = [ev() for _ in range(2 * len(QLEVELS) + 1)] if record else None
+        if record:
+            row[0].record(stream)
+        for i, enc in enumerate(encs):
+            enc.encode_device(frames, grids_out=grids)
+            if record:
+                row[2 * i + 1].record(stream)
+            dec.decode_device(LEVELS, grids, images_out=back)
+            if record:
+                row[2 * i + 2].record(stream)
+        if record:
+            marks.append(row)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                                     # started early: nvidia-smi takes a while to come up
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    wall0 = time.time()
+    launches0 = ctx.kernel_launches
+    t_begin, t_end = ev(), ev()
+    t_begin.record(stream)
+    for _ in range(args.steps):
+        step(True)
+    t_end.record(stream)
+    barrier()
+    clocks = sampler.stop(wall0, time.time()) if rank == 0 else None
+    launches = ctx.kernel_launches - launches0
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    if dist:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    px_step = len(QLEVELS) * frames_n * W * H
+    value = world * px_step / (ms_per_step * 1e-3) / 1e6
+
+    # per-kernel durations (L=4 => each encode / decode is exactly one kernel launch)
+    names = ["encode_lossless", "decode_lossless", "encode_medium", "decode_medium"]
+    per = {n: statistics.mean(r[i].elapsed_time(r[i + 1]) for r in marks) for i, n in enumerate(names)}
+
+    # sanity: the timed outputs are real (last pass was Medium): bounded error, seeds raw
+    err = int((back[:8].to(torch.int16) - frames[:8].to(torch.int16)).abs().max().item())
+    assert err <= 20 and torch.equal(back[:8, ::16, ::16], frames[:8, ::16, ::16]), "bench output failed sanity"
+
+    # ---- e2e: host-pointer C-ABI calls, pinned host memory, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        del back
+        torch.cuda.empty_cache()
+        n_e = min(args.e2e_frames or 1024, frames_n)        # pinned buffer size (frames); see e2e_step
+        n_sub = -(-frames_n // n_e)                         # sub-batches per step: the whole workload streams through
+        try:
+            h_in = torch.empty((n_e, H, W), dtype=torch.uint8, pin_memory=True)
+            h_grid = torch.empty((n_e, H, W), dtype=torch.uint8, pin_memory=True)
+            h_out = torch.empty((n_e, H, W), dtype=torch.uint8, pin_memory=True)
+        except Exception as exc:                            # pinned allocation refused: say so
+            h_in = None
+            e2e = {"value": None, "unit": UNIT, "error": f"pinned allocation failed: {exc}"}
+        if h_in is not None:
+            h_in.copy_(frames[:n_e])
+            torch.cuda.synchronize()
+            a_in, a_grid, a_out = h_in.numpy(), h_grid.numpy(), h_out.numpy()
+            import ctypes
+            L = hgi.lib()
+
+            def e2e_step():
+                # the step's frames_n frames go through the host API as n_sub calls on one pinned
+                # buffer set of n_e frames (host RAM on the box is 196 GB for 8 ranks)
+                for enc in encs:
+                    p = enc._p()
+                    for _ in range(n_sub):
+                        ctx.check(L.hgi_encode_batch_u8(ctx._h, a_in.ctypes.data, n_e, W, H, ctypes.byref(p),
+                                                        a_grid.ctypes.data, None), "hgi_encode_batch_u8")
+                        ctx.check(L.hgi_decode_batch_u8(ctx._h, a_grid.ctypes.data, n_e, W, H, ctypes.byref(p),
+                                                        a_out.ctypes.data), "hgi_decode_batch_u8")
+
+            e_steps = max(1, min(args.steps, 3))
+            e2e_step()                                      # warm-up (allocates the staging slots)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                e2e_step()
+            barrier()
+            dt = (time.perf_counter() - t0) / e_steps
+            if dist:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            assert int((h_out[:4].to(torch.int16) - h_in[:4].to(torch.int16)).abs().max().item()) <= 20
+            f_e = n_sub * n_e
+            bytes_dir = len(QLEVELS) * 2 * f_e * W * H      # encode in + decode in / encode out + decode out
+            e2e = {"value": world * len(QLEVELS) * f_e * W * H / dt / 1e6, "unit": UNIT,
+                   "h2d_bytes_per_step": bytes_dir, "d2h_bytes_per_step": bytes_dir, "frames_per_gpu": f_e,
+                   "pinned_buffer_frames": n_e,
+                   "steps": e_steps, "ms_per_step": dt * 1e3,
+                   "api": "hgi_encode_batch_u8 + hgi_decode_batch_u8 (host pointers, pinned)"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg_bytes = 2.0 * frames_n * W * H                  # 2 B/pixel: read pixel + write residual
+        dom = "encode_medium"
+        achieved = alg_bytes / (per[dom] * 1e-3) / 1e9
+        traffic = profiled_traffic()
+        roofline = {"bound": "hbm", "kernel": "hgi_tile_kernel<encode, Crossed, Linear> (Medium)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                    "ms_per_launch": per[dom],
+                    "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                    "traffic_source": traffic.get("source") if traffic else None,
+                    "per_kernel": {n: {"ms": per[n], "GB/s": alg_bytes / (per[n] * 1e-3) / 1e9,
+                                       "frac": alg_bytes / (per[n] * 1e-3) / 1e9 / peak} for n in names}}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(frames_n, world),
+                "roofline": roofline, "cpu_baseline": None if args.no_cpu else cpu_baseline(), "e2e": e2e,
+                "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU (default: the named workload)")
+    ap.add_argument("--e2e-frames", type=int, default=0, help="frames in the pinned e2e buffers (default 1024)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1 and "RANK" not in os.environ:
+        # launched without torchrun: start one rank per GPU ourselves
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

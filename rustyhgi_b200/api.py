@@ -155,6 +155,14 @@ def _host_planes(a, what):
     return np.ascontiguousarray(a)
 
 
+def _stream_handle(stream, device):
+    """cudaStream_t for the C ABI.  The ABI reads NULL as "the context's own stream", so torch's
+    legacy default stream (handle 0) is passed as cudaStreamLegacy (0x1)."""
+    import torch
+    h = stream if stream is not None else torch.cuda.current_stream(device).cuda_stream
+    return h if h else 1
+
+
 class Grid:
     """src/grid.rs:1-5: `buffer` (row-major u8, stride = width) + `width`."""
 
@@ -227,7 +235,7 @@ class Encoder:
         if grids_out is None:
             grids_out = torch.empty_like(t)
         assert grids_out.is_contiguous() and grids_out.numel() == t.numel()
-        st = stream if stream is not None else torch.cuda.current_stream(t.device).cuda_stream
+        st = _stream_handle(stream, t.device)
         p = self._p()
         rc = _lib.lib().hgi_encode_dev(self.ctx._h, t.data_ptr(), n, w, h, ctypes.byref(p), grids_out.data_ptr(),
                                        recon_out.data_ptr() if recon_out is not None else None,
@@ -276,7 +284,7 @@ class Decoder:
         n, h, w = t.shape
         if images_out is None:
             images_out = torch.empty_like(t)
-        st = stream if stream is not None else torch.cuda.current_stream(t.device).cuda_stream
+        st = _stream_handle(stream, t.device)
         p = _params(levels, self._interp)
         rc = _lib.lib().hgi_decode_dev(self.ctx._h, t.data_ptr(), n, w, h, ctypes.byref(p), images_out.data_ptr(), st)
         self.ctx.check(rc, "hgi_decode_dev")
