@@ -71,7 +71,8 @@ typedef enum {
 /* Which CUDA path a context uses.  Both produce identical bytes. */
 typedef enum {
     HGI_PATH_TILE = 0,      /* default: fused multi-level shared-memory tile kernels */
-    HGI_PATH_PER_LEVEL = 1  /* one kernel per level over HBM (north_star's literal shape) */
+    HGI_PATH_PER_LEVEL = 1, /* one kernel per level over HBM (north_star's literal shape) */
+    HGI_PATH_TILE_GENERIC = 2 /* fused tiles, but always the generic (scalar, any alignment) kernel */
 } hgi_path_t;
 
 #define HGI_MAX_LEVELS 31u

@@ -194,7 +194,7 @@ int run_tile_path(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images,
             a.s_recon = ctx->compact[set].p;
             a.s_q = ctx->compact[set + 1].p;
         }
-        HGI_CUDA(ctx, hgi::launch_tile_pass(mode, prm->interp, a, st));
+        HGI_CUDA(ctx, hgi::launch_tile_pass(mode, prm->interp, a, st, ctx->path == HGI_PATH_TILE_GENERIC));
         ctx->launches++;
         c_recon = a.s_recon;
         c_q = a.s_q;
@@ -374,6 +374,7 @@ int hgi_ctx_create(int device, hgi_ctx_t** ctx_out)
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return HGI_ERR_NO_DEVICE;
     if (prop.major != 10) return HGI_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+    if (!hgi::quant_swar_self_check()) return HGI_ERR_UNSUPPORTED;  // SWAR quantizer != reference table
     hgi_ctx* ctx = new (std::nothrow) hgi_ctx();
     if (!ctx) return HGI_ERR_ALLOC;
     ctx->device = device;
@@ -413,7 +414,7 @@ void hgi_ctx_destroy(hgi_ctx_t* ctx)
 
 int hgi_ctx_set_path(hgi_ctx_t* ctx, int path)
 {
-    if (!ctx || (path != HGI_PATH_TILE && path != HGI_PATH_PER_LEVEL)) return HGI_ERR_INVALID_ARG;
+    if (!ctx || path < HGI_PATH_TILE || path > HGI_PATH_TILE_GENERIC) return HGI_ERR_INVALID_ARG;
     ctx->path = path;
     return HGI_OK;
 }

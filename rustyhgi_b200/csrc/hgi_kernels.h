@@ -34,7 +34,12 @@ struct PassArgs {
     uint32_t vec_ok;         // D==1 and rows are 16-byte aligned => 128-bit global accesses
 };
 
-cudaError_t launch_tile_pass(int mode, int interp, const PassArgs& args, cudaStream_t stream);
+// Dispatches to the fast kernel (hgi_tile_fast.cu) for D == 1 passes on 16-byte-aligned planes and
+// to the generic kernel (hgi_tile_kernels.cu) otherwise.  `force_generic` is a test hook.
+cudaError_t launch_tile_pass(int mode, int interp, const PassArgs& args, cudaStream_t stream,
+                             bool force_generic = false);
+cudaError_t launch_tile_pass_fast(int mode, int interp, const PassArgs& args, cudaStream_t stream);
+bool quant_swar_self_check();
 
 // ---- per-level path -----------------------------------------------------------------------
 struct LevelArgs {
