@@ -66,11 +66,20 @@ __device__ __forceinline__ uint32_t avg2(uint32_t x, uint32_t y)   // src/interp
 {
     return ((x + y + 0x00010001u) >> 1) & M16;
 }
+// src/interpolator.rs:43-54 per lane.  With avg(x,y) = (x+y+1)>>1 = (x + y + ((x^y)&1)) / 2, the sum of the
+// four edge averages is T + E/2 where T = A+B+C+D and E counts the edges of the cycle A-B-D-C-A whose
+// endpoints differ in parity (E is 0, 2 or 4).  With u = (A^B)&1, v = (C^D)&1:
+//   E/2 = (u|v) + (!(u^v) & (A^C)&1)
+// which is checked exhaustively against the four-average form in tests/test_swar_model.py.  This needs
+// 10 ALU-pipe operations per register instead of 16.
 template <int INTERP>
 __device__ __forceinline__ uint32_t pred2(uint32_t A, uint32_t B, uint32_t C, uint32_t D)
 {
     if (INTERP == kInterpLeftTop) return A;                                    // src/interpolator.rs:26
-    const uint32_t sum = avg2(A, B) + avg2(D, C) + avg2(C, A) + avg2(D, B);   // :46-49, lanes <= 1020
+    const uint32_t x1 = A ^ B;
+    const uint32_t t1 = x1 | (C ^ D);
+    const uint32_t t2 = ~(x1 ^ C ^ D) & (A ^ C);
+    const uint32_t sum = (A + B + C) + (D + (t1 & 0x00010001u) + (t2 & 0x00010001u));   // lanes <= 1022
     return (sum >> 2) & M16;                                                   // :51
 }
 
@@ -95,9 +104,9 @@ __host__ __device__ inline QuantSwar quant_swar(uint32_t error)
 
 // src/encoder.rs:52-64 for two pixels.  Returns the symbols; `recon` = what the decoder rebuilds.
 template <bool IDENTITY>
-__device__ __forceinline__ uint32_t encode2(uint32_t a, uint32_t p, const QuantSwar& qc, uint32_t& recon)
+__device__ __forceinline__ uint32_t encode2(uint32_t a, uint32_t p, uint32_t pk, const QuantSwar& qc, uint32_t& recon)
 {
-    const uint32_t dd = a + 0x01000100u - p;          // per lane a + 256 - p: bit 8 = [a >= p]
+    const uint32_t dd = a + pk;                       // pk = 0x01000100 - p: per lane a + 256 - p, bit 8 = [a >= p]
     const uint32_t d = dd & M16;                      // :53 wrapping_sub
     if (IDENTITY) {
         recon = a;                                    // p + (a - p) == a
@@ -106,7 +115,7 @@ __device__ __forceinline__ uint32_t encode2(uint32_t a, uint32_t p, const QuantS
     const uint32_t t = d * qc.mul + qc.add;
     const uint32_t r = (t >> qc.shift) & 0x000F000Fu;
     uint32_t q = r * qc.scale;                        // :54 table[d]
-    const uint32_t ov = p + q;                        // bit 8 = overflow                      (:56)
+    const uint32_t ov = r * qc.scale + p;             // p + q, bit 8 = overflow               (:56)
     // overflow_is_expected = [a < p] = !bit8(dd)  =>  mismatch iff bit8(ov) == bit8(dd)       (:57-58)
     const uint32_t x = ~(ov ^ dd) & 0x01000100u;
     const uint32_t m = x - (x >> 8);                  // 0x00FF in every mismatching lane
@@ -131,7 +140,8 @@ struct FastSmem {
 
 // Stage one 16-byte chunk (columns 16c..16c+15 of tile row y, y even) into the dense planes of the
 // levels that are computed in this pass (s < F).  c == 8 is the right-halo chunk (x = TW..TW+15).
-__device__ __forceinline__ void stage_chunk(uint8_t* P, const uint4 v, int y, int c, int F)
+template <int F>
+__device__ __forceinline__ void stage_chunk(uint8_t* P, const uint4 v, int y, int c)
 {
     if (F > 2 && y <= TH) {
         uint8_t* row = P + plane_off(2) + (y >> 1) * plane_pitch(2);
@@ -172,9 +182,10 @@ __device__ __forceinline__ void level_word(FastSmem& sm, int g, int cy, const Qu
     const uint32_t a1 = lanes_odd(ev), a2 = lanes_even(od), a3 = lanes_odd(od);
     uint32_t r1, r2, r3;
     if (MODE == kModeEncode) {
-        const uint32_t q1 = encode2<IDENTITY>(a1, p, qc, r1);
-        const uint32_t q2 = encode2<IDENTITY>(a2, p, qc, r2);
-        const uint32_t q3 = encode2<IDENTITY>(a3, p, qc, r3);
+        const uint32_t pk = 0x01000100u - p;
+        const uint32_t q1 = encode2<IDENTITY>(a1, p, pk, qc, r1);
+        const uint32_t q2 = encode2<IDENTITY>(a2, p, pk, qc, r2);
+        const uint32_t q3 = encode2<IDENTITY>(a3, p, pk, qc, r3);
         uint8_t* Qs = sm.Q + plane_off(S);
         const uint8_t* Qc = sm.Q + plane_off(2 * S);
         const uint32_t QA = lanes01((uint32_t)*reinterpret_cast<const uint16_t*>(Qc + cy * pc + 2 * g));
@@ -251,66 +262,70 @@ __device__ __forceinline__ void coarse_level(FastSmem& sm, int tid, const QuantS
     __syncthreads();
 }
 
-template <int MODE, int INTERP, bool IDENTITY, bool EXTRA>
-__global__ void __launch_bounds__(NT, 4)
+#ifndef HGI_FAST_MIN_BLOCKS
+#define HGI_FAST_MIN_BLOCKS 8
+#endif
+
+template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV>
+__global__ void __launch_bounds__(NT, HGI_FAST_MIN_BLOCKS)
 hgi_tile_fast_kernel(const PassArgs p)
 {
     __shared__ FastSmem sm;
     __shared__ uint32_t whist[(MODE == kModeEncode && EXTRA) ? NWARPS * 256 : 1];
+    constexpr int F = 1 << NLEV;
 
     const int tid = threadIdx.x;
     const uint32_t img = blockIdx.z;
-    const int X0 = (int)(blockIdx.x * TW), Y0 = (int)(blockIdx.y * TH);
-    const int xin = (int)min((uint32_t)(TW + FMAX + 1), p.w - (uint32_t)X0);   // in-image extent of tile + halo
-    const int yin = (int)min((uint32_t)(TH + FMAX + 1), p.h - (uint32_t)Y0);
+    const uint32_t X0 = blockIdx.x * TW, Y0 = blockIdx.y * TH;
+    const int xin = (int)min((uint32_t)(TW + FMAX + 1), p.w - X0);   // in-image extent of tile + halo
+    const int yin = (int)min((uint32_t)(TH + FMAX + 1), p.h - Y0);
     const bool edge = (xin < TW + FMAX + 1) || (yin < TH + FMAX + 1);
-    const size_t plane = (size_t)p.w * p.h;
-    const uint8_t* __restrict__ src = p.src + (size_t)img * plane;
+    const size_t tile_off = ((size_t)img * p.h + Y0) * p.w + X0;     // CTA-uniform
+    const uint8_t* __restrict__ tile = p.src + tile_off;
     const bool top = (p.c_recon == nullptr);
-    const int F = 1 << p.nlev;
     const QuantSwar qc = quant_swar(p.quant_error);
 
     // ---- 1. global loads: this thread's 16x2 pixels (kept in registers for the finest level) ----
     const int sx = tid & 7, ry = tid >> 3;          // 8 column strips x 32 row pairs
     const bool col_ok = 16 * sx < xin;
     const bool row0_ok = 2 * ry < yin, row1_ok = 2 * ry + 1 < yin;
-    const size_t goff = (size_t)(Y0 + 2 * ry) * p.w + (size_t)(X0 + 16 * sx);
+    const uint32_t toff = (uint32_t)(2 * ry) * p.w + (uint32_t)(16 * sx);   // tile-relative, fits 32 bits
     uint4 ev = make_uint4(0u, 0u, 0u, 0u), od = make_uint4(0u, 0u, 0u, 0u);
-    if (col_ok && row0_ok) ev = __ldg(reinterpret_cast<const uint4*>(src + goff));
-    if (col_ok && row1_ok) od = __ldg(reinterpret_cast<const uint4*>(src + goff + p.w));
+    if (col_ok && row0_ok) ev = __ldg(reinterpret_cast<const uint4*>(tile + toff));
+    if (col_ok && row1_ok) od = __ldg(reinterpret_cast<const uint4*>(tile + toff + p.w));
 
-    // halo chunks (right of / below the tile) feed only the coarse planes; the last two warps fetch them
-    int hy = -1, hc = 0;
-    if (tid >= NT - 64) {
-        const int j = tid - (NT - 64);
-        if (j < 33) { hy = 2 * j; hc = 8; }
-        else if (j < 41) { hy = TH; hc = j - 33; }
-        else if (j < 50) { hy = TH + 4; hc = j - 41; }
-        else if (j < 59) { hy = TH + 8; hc = j - 50; }
+    // halo chunks (right of / below the tile) feed only the coarse planes; the last two warps fetch
+    // them: 32 right-halo chunks (rows 0,2,..,TH-2; column TW) + rows TH, TH+4, TH+8 (chunks 0..8)
+    const int hj = tid - (NT - 64);
+    int hy = 2 * hj, hc = 8;
+    if (hj >= 32) {
+        const int r = (hj - 32) / 9;
+        hc = (hj - 32) - 9 * r;
+        hy = TH + 4 * r;
     }
+    const bool halo = NLEV > 1 && hj >= 0 && hj < 59;
     uint4 hv = make_uint4(0u, 0u, 0u, 0u);
-    if (hy >= 0 && hy < yin && 16 * hc < xin)
-        hv = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(Y0 + hy) * p.w + (size_t)(X0 + 16 * hc)));
+    if (halo && hy < yin && 16 * hc < xin)
+        hv = __ldg(reinterpret_cast<const uint4*>(tile + (uint32_t)hy * p.w + (uint32_t)(16 * hc)));
 
     // ---- 2. stage the dense coarse planes + the coarse lattice of this pass ---------------------
-    stage_chunk(sm.P, ev, 2 * ry, sx, F);
-    if (hy >= 0) stage_chunk(sm.P, hv, hy, hc, F);
+    stage_chunk<F>(sm.P, ev, 2 * ry, sx);
+    if (halo) stage_chunk<F>(sm.P, hv, hy, hc);
     {
-        const int ncx = TW / F + 2, ncy = TH / F + 2;
+        constexpr int ncx = TW / F + 2, ncy = TH / F + 2;
+        constexpr int pf = plane_pitch(F);
         uint8_t* Pf = sm.P + plane_off(F);
         uint8_t* Qf = sm.Q + plane_off(F);
-        const int pf = plane_pitch(F);
         for (int it = tid; it < ncx * ncy; it += NT) {
             const int cj = it / ncx, ci = it - cj * ncx;
             const int x = ci * F, y = cj * F;
             uint8_t rv = 0, qv = 0;
             if (x < xin && y < yin) {
                 if (top) {   // src/encoder.rs:26-37 / src/decoder.rs:22-28: the seed is the source byte
-                    rv = __ldg(src + (size_t)(Y0 + y) * p.w + (size_t)(X0 + x));
+                    rv = __ldg(tile + (uint32_t)y * p.w + (uint32_t)x);
                     qv = rv;
                 } else {
-                    const size_t co = (size_t)img * p.cw * p.ch + (size_t)((uint32_t)(Y0 + y) >> p.nlev) * p.cw +
-                                      ((uint32_t)(X0 + x) >> p.nlev);
+                    const size_t co = (size_t)img * p.cw * p.ch + (size_t)((Y0 + y) >> NLEV) * p.cw + ((X0 + x) >> NLEV);
                     rv = __ldg(p.c_recon + co);
                     if (MODE == kModeEncode) qv = __ldg(p.c_q + co);
                 }
@@ -347,9 +362,10 @@ hgi_tile_fast_kernel(const PassArgs p)
         const uint32_t a1 = lanes_odd(evw[k]), a2 = lanes_even(odw[k]), a3 = lanes_odd(odw[k]);
         if (MODE == kModeEncode) {
             uint32_t r1, r2, r3;
-            const uint32_t q1 = encode2<IDENTITY>(a1, pr, qc, r1);
-            const uint32_t q2 = encode2<IDENTITY>(a2, pr, qc, r2);
-            const uint32_t q3 = encode2<IDENTITY>(a3, pr, qc, r3);
+            const uint32_t pk = 0x01000100u - pr;
+            const uint32_t q1 = encode2<IDENTITY>(a1, pr, pk, qc, r1);
+            const uint32_t q2 = encode2<IDENTITY>(a2, pr, pk, qc, r2);
+            const uint32_t q3 = encode2<IDENTITY>(a3, pr, pk, qc, r3);
             const uint32_t qw = (k < 2) ? qcw.x : qcw.y;
             const uint32_t QA = (k & 1) ? lanes23(qw) : lanes01(qw);
             out_ev[k] = interleave(QA, q1);
@@ -363,14 +379,14 @@ hgi_tile_fast_kernel(const PassArgs p)
             out_od[k] = interleave(decode2(a2, pr), decode2(a3, pr));
         }
     }
-    uint8_t* __restrict__ out = (MODE == kModeEncode ? p.grid_out : p.recon_out) + (size_t)img * plane;
-    if (col_ok && row0_ok) *reinterpret_cast<uint4*>(out + goff) = make_uint4(out_ev[0], out_ev[1], out_ev[2], out_ev[3]);
-    if (col_ok && row1_ok) *reinterpret_cast<uint4*>(out + goff + p.w) = make_uint4(out_od[0], out_od[1], out_od[2], out_od[3]);
+    uint8_t* __restrict__ out = (MODE == kModeEncode ? p.grid_out : p.recon_out) + tile_off;
+    if (col_ok && row0_ok) *reinterpret_cast<uint4*>(out + toff) = make_uint4(out_ev[0], out_ev[1], out_ev[2], out_ev[3]);
+    if (col_ok && row1_ok) *reinterpret_cast<uint4*>(out + toff + p.w) = make_uint4(out_od[0], out_od[1], out_od[2], out_od[3]);
     if (MODE == kModeEncode && EXTRA) {
         if (p.recon_out != nullptr) {
-            uint8_t* __restrict__ rout = p.recon_out + (size_t)img * plane;
-            if (col_ok && row0_ok) *reinterpret_cast<uint4*>(rout + goff) = make_uint4(rec_ev[0], rec_ev[1], rec_ev[2], rec_ev[3]);
-            if (col_ok && row1_ok) *reinterpret_cast<uint4*>(rout + goff + p.w) = make_uint4(rec_od[0], rec_od[1], rec_od[2], rec_od[3]);
+            uint8_t* __restrict__ rout = p.recon_out + tile_off;
+            if (col_ok && row0_ok) *reinterpret_cast<uint4*>(rout + toff) = make_uint4(rec_ev[0], rec_ev[1], rec_ev[2], rec_ev[3]);
+            if (col_ok && row1_ok) *reinterpret_cast<uint4*>(rout + toff + p.w) = make_uint4(rec_od[0], rec_od[1], rec_od[2], rec_od[3]);
         }
         // residual histogram (north_star's archive.rs stage): warp-private bins, one global atomic per
         // non-empty bin per tile
@@ -397,8 +413,8 @@ hgi_tile_fast_kernel(const PassArgs p)
     }
 }
 
-template <int MODE, int INTERP>
-cudaError_t launch_fast_t(const PassArgs& args, cudaStream_t stream)
+template <int MODE, int INTERP, int NLEV>
+cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
 {
     if (args.tiles_x == 0 || args.tiles_y == 0 || args.n_images == 0) return cudaSuccess;
     if (args.tiles_y > 65535u) return cudaErrorInvalidConfiguration;
@@ -414,19 +430,31 @@ cudaError_t launch_fast_t(const PassArgs& args, cudaStream_t stream)
         if (args.c_q) a.c_q = args.c_q + (size_t)first * args.cw * args.ch;
         const dim3 nb(a.tiles_x, a.tiles_y, a.n_images);
         if (MODE == kModeDecode) {
-            hgi_tile_fast_kernel<kModeDecode, INTERP, true, false><<<nb, NT, 0, stream>>>(a);
+            hgi_tile_fast_kernel<kModeDecode, INTERP, true, false, NLEV><<<nb, NT, 0, stream>>>(a);
         } else {
             const bool extra = (a.recon_out != nullptr) || (a.hist != nullptr);
             const bool ident = (a.quant_error == 0);
-            if (ident && !extra) hgi_tile_fast_kernel<kModeEncode, INTERP, true, false><<<nb, NT, 0, stream>>>(a);
-            else if (ident) hgi_tile_fast_kernel<kModeEncode, INTERP, true, true><<<nb, NT, 0, stream>>>(a);
-            else if (!extra) hgi_tile_fast_kernel<kModeEncode, INTERP, false, false><<<nb, NT, 0, stream>>>(a);
-            else hgi_tile_fast_kernel<kModeEncode, INTERP, false, true><<<nb, NT, 0, stream>>>(a);
+            if (ident && !extra) hgi_tile_fast_kernel<kModeEncode, INTERP, true, false, NLEV><<<nb, NT, 0, stream>>>(a);
+            else if (ident) hgi_tile_fast_kernel<kModeEncode, INTERP, true, true, NLEV><<<nb, NT, 0, stream>>>(a);
+            else if (!extra) hgi_tile_fast_kernel<kModeEncode, INTERP, false, false, NLEV><<<nb, NT, 0, stream>>>(a);
+            else hgi_tile_fast_kernel<kModeEncode, INTERP, false, true, NLEV><<<nb, NT, 0, stream>>>(a);
         }
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+
+template <int MODE, int INTERP>
+cudaError_t launch_fast_t(const PassArgs& a, cudaStream_t stream)
+{
+    switch (a.nlev) {
+        case 1: return launch_fast_n<MODE, INTERP, 1>(a, stream);
+        case 2: return launch_fast_n<MODE, INTERP, 2>(a, stream);
+        case 3: return launch_fast_n<MODE, INTERP, 3>(a, stream);
+        case 4: return launch_fast_n<MODE, INTERP, 4>(a, stream);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 }  // namespace

@@ -1,0 +1,87 @@
+"""Bit-level model of the 16-bit-lane SWAR arithmetic in rustyhgi_b200/csrc/hgi_tile_fast.cu,
+checked exhaustively against the reference formulas (CPU only).  The device code uses exactly
+these word operations; the GPU parity tests check the code, this checks the algebra."""
+import itertools
+
+import numpy as np
+
+from oracle import c as oc
+
+M16 = 0x00FF00FF
+U32 = 0xFFFFFFFF
+
+
+def ref_pred(A, B, C, D):
+    avg = lambda x, y: (x + y + 1) >> 1                      # src/interpolator.rs:44
+    return (avg(A, B) + avg(D, C) + avg(C, A) + avg(D, B)) >> 2
+
+
+def swar_pred(A, B, C, D):                                    # pred2<Crossed>
+    x1 = A ^ B
+    t1 = x1 | (C ^ D)
+    t2 = (~(x1 ^ C ^ D) & U32) & (A ^ C)
+    s = (A + B + C) + (D + (t1 & 0x00010001) + (t2 & 0x00010001))
+    return (s >> 2) & M16
+
+
+def test_parity_predictor_all_low_bit_patterns_and_ranges():
+    vals = [0, 1, 2, 3, 4, 5, 126, 127, 128, 129, 252, 253, 254, 255]
+    for A, B, C, D in itertools.product(vals, repeat=4):
+        assert swar_pred(A, B, C, D) == ref_pred(A, B, C, D)
+    rng = np.random.default_rng(0)
+    q = rng.integers(0, 256, (200000, 8))
+    for A, B, C, D, A2, B2, C2, D2 in q[:20000]:
+        lanes = swar_pred(int(A | (A2 << 16)), int(B | (B2 << 16)), int(C | (C2 << 16)), int(D | (D2 << 16)))
+        assert lanes & 0xFFFF == ref_pred(A, B, C, D) and lanes >> 16 == ref_pred(A2, B2, C2, D2)
+
+
+QUANT = {10: (195, 195, 12), 20: (25, 0, 10), 30: (67, 67, 12)}   # quant_swar()
+
+
+def swar_encode2(a, p, error):
+    """encode2<false>: returns (q lanes, recon lanes)."""
+    k, c, n = QUANT[error]
+    scale = 2 * error + 1
+    add = ((error * k + c) * 0x00010001) & U32
+    pk = (0x01000100 - p) & U32
+    dd = (a + pk) & U32
+    d = dd & M16
+    t = (d * k + add) & U32
+    r = (t >> n) & 0x000F000F
+    q = (r * scale) & U32
+    ov = (r * scale + p) & U32
+    x = (~(ov ^ dd)) & 0x01000100
+    m = (x - (x >> 8)) & U32
+    q = (q & ~m & U32) | (d & m)
+    recon = ((ov & ~m) | (a & m)) & M16
+    return q, recon
+
+
+def ref_encode(a, p, table):
+    d = (a - p) & 255                                          # src/encoder.rs:53
+    q = int(table[d])                                          # :54
+    if ((p + q) > 255) != ((p + d) > 255):                     # :56-58
+        q = d
+    return q, (p + q) & 255
+
+
+def test_swar_encode_point_exhaustive():
+    """All (a, p) pairs in both lanes, every Linear level: symbol and reconstruction."""
+    for level, error in ((1, 10), (2, 20), (3, 30)):
+        table, _ = oc.quant_table(oc.QUANT_LINEAR, level)
+        for p0 in range(256):
+            p1 = 255 - p0
+            for a0 in range(256):
+                a1 = (a0 * 7 + 13) & 255
+                q, r = swar_encode2(a0 | (a1 << 16), p0 | (p1 << 16), error)
+                q0, r0 = ref_encode(a0, p0, table)
+                q1, r1 = ref_encode(a1, p1, table)
+                assert (q & 0xFFFF, r & 0xFFFF, q >> 16, r >> 16) == (q0, r0, q1, r1), (level, a0, p0)
+
+
+def test_swar_quantizer_constants_are_exact():
+    for error, (k, c, n) in QUANT.items():
+        scale = 2 * error + 1
+        for d in range(256):
+            t = d * k + error * k + c
+            assert t < 65536 and ((t >> n) & 15) * scale == ((d + error) // scale) * scale
