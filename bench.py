@@ -314,7 +314,7 @@ def run_ours(args, rank, world, local_rank):
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                     "ms_per_launch": per[dom],
-                    "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                    "traffic": traffic["dram_bytes_per_pixel"] * frames_n * W * H if traffic else None,
                     "traffic_source": traffic.get("source") if traffic else None,
                     "per_kernel": {n: {"ms": per[n], "GB/s": alg_bytes / (per[n] * 1e-3) / 1e9,
                                        "frac": alg_bytes / (per[n] * 1e-3) / 1e9 / peak} for n in names}}
@@ -333,7 +333,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU (default: the named workload)")
