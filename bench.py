@@ -176,6 +176,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("HGI_BENCH_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)

@@ -24,24 +24,30 @@ namespace hgi {
 
 namespace {
 
-constexpr int TW = kTileW;
-constexpr int TH = kTileH;
-constexpr int NT = kTileThreads;
+#ifndef HGI_FAST_TILE_H
+#define HGI_FAST_TILE_H 128
+#endif
+constexpr int TW = 128;                  // tile width  (lattice points)
+constexpr int TH = HGI_FAST_TILE_H;      // tile height: 64 or 128 (NU = TH/64 16x2 units per thread)
+constexpr int NT = 256;
+constexpr int NU = TH / 64;
 constexpr int NWARPS = NT / 32;
 constexpr int FMAX = 1 << kMaxPassLevels;
 constexpr uint32_t M16 = 0x00FF00FFu;
 
-static_assert(TW == 128 && TH == 64 && NT == 256, "thread mapping below assumes 128x64 tiles, 256 threads");
+static_assert(TW == 128 && (TH == 64 || TH == 128) && NT == 256, "thread mapping assumes 128-wide tiles, 256 threads");
 
 // Dense level planes.  P_s holds lattice-s points of the tile + halo: columns 0..TW/s+1,
 // rows 0..TH/s+1 (the last ones are only partially needed, see need_limit).
 __host__ __device__ constexpr int plane_pitch(int s) { return s == 2 ? 96 : (s == 4 ? 48 : (s == 8 ? 32 : 16)); }
 __host__ __device__ constexpr int plane_rows(int s) { return TH / s + 2; }
+__host__ __device__ constexpr int plane_bytes(int s) { return plane_rows(s) * plane_pitch(s); }
 __host__ __device__ constexpr int plane_off(int s)
 {
-    return s == 2 ? 0 : (s == 4 ? 34 * 96 : (s == 8 ? 34 * 96 + 18 * 48 : 34 * 96 + 18 * 48 + 10 * 32));
+    return s == 2 ? 0 : (s == 4 ? plane_bytes(2) : (s == 8 ? plane_bytes(2) + plane_bytes(4)
+                                                               : plane_bytes(2) + plane_bytes(4) + plane_bytes(8)));
 }
-constexpr int PLANE_BYTES = 34 * 96 + 18 * 48 + 10 * 32 + 6 * 16;  // 4544
+constexpr int PLANE_BYTES = plane_bytes(2) + plane_bytes(4) + plane_bytes(8) + plane_bytes(16);  // 4544 (TH=64) / 8704 (TH=128)
 
 __device__ __forceinline__ int need_limit(int tile_extent, int s)
 {
@@ -67,25 +73,26 @@ __device__ __forceinline__ uint32_t avg2(uint32_t x, uint32_t y)   // src/interp
     return ((x + y + 0x00010001u) >> 1) & M16;
 }
 // src/interpolator.rs:43-54 per lane.  With avg(x,y) = (x+y+1)>>1 = (x + y + ((x^y)&1)) / 2, the sum of the
-// four edge averages is T + E/2 where T = A+B+C+D and E counts the edges of the cycle A-B-D-C-A whose
-// endpoints differ in parity (E is 0, 2 or 4).  With u = (A^B)&1, v = (C^D)&1:
-//   E/2 = (u|v) + (!(u^v) & (A^C)&1)
-// which is checked exhaustively against the four-average form in tests/test_swar_model.py.  This needs
-// 10 ALU-pipe operations per register instead of 16.
+// four edge averages is T + E/2, T = A+B+C+D, where E counts the edges of the cycle A-B-D-C-A whose
+// endpoints differ in parity (0, 2 or 4).  Working through floor((T + E/2)/4) by the parity of T gives
+//     pred = (((T + 1) >> 1) + w) >> 1,    w = (A^B) & (C^D) & (A^C) & 1
+// (E/2 only matters when it makes T+E/2 cross a multiple of 4: T odd -> the +1; T = 2 mod 4 with all
+// three parity tests true -> the w).  Checked against the four-average form in tests/test_swar_model.py.
+// 8 ALU-pipe operations per register (two cells) instead of 16.
 template <int INTERP>
 __device__ __forceinline__ uint32_t pred2(uint32_t A, uint32_t B, uint32_t C, uint32_t D)
 {
     if (INTERP == kInterpLeftTop) return A;                                    // src/interpolator.rs:26
-    const uint32_t x1 = A ^ B;
-    const uint32_t t1 = x1 | (C ^ D);
-    const uint32_t t2 = ~(x1 ^ C ^ D) & (A ^ C);
-    const uint32_t sum = (A + B + C) + (D + (t1 & 0x00010001u) + (t2 & 0x00010001u));   // lanes <= 1022
-    return (sum >> 2) & M16;                                                   // :51
+    const uint32_t x1 = (A ^ B) & 0x00010001u;
+    const uint32_t w = x1 & (C ^ D) & (A ^ C);
+    const uint32_t h = ((A + B + C) + (D + 0x00010001u)) >> 1;                 // lanes <= 510 (+ stray bit 15)
+    return ((h + w) >> 1) & M16;                                               // :51
 }
 
 // Linear quantizer as an exact per-lane multiply-shift: ((d + e) / scale) * scale for d in 0..255.
 struct QuantSwar {
     uint32_t mul, add, shift, scale;
+    uint32_t rmask, qmul;   // q = umulhi(t & rmask, qmul): rmask = 0xF << shift per lane, qmul = scale << (32 - shift)
 };
 __host__ __device__ inline QuantSwar quant_swar(uint32_t error)
 {
@@ -99,6 +106,8 @@ __host__ __device__ inline QuantSwar quant_swar(uint32_t error)
     q.add = (error * k + c) * 0x00010001u;
     q.shift = n;
     q.scale = 2 * error + 1;
+    q.rmask = (0xFu << n) * 0x00010001u;
+    q.qmul = n ? (q.scale << (32 - n)) : 0u;
     return q;
 }
 
@@ -112,13 +121,14 @@ __device__ __forceinline__ uint32_t encode2(uint32_t a, uint32_t p, uint32_t pk,
         recon = a;                                    // p + (a - p) == a
         return d;
     }
-    const uint32_t t = d * qc.mul + qc.add;
-    const uint32_t r = (t >> qc.shift) & 0x000F000Fu;
-    uint32_t q = r * qc.scale;                        // :54 table[d]
-    const uint32_t ov = r * qc.scale + p;             // p + q, bit 8 = overflow               (:56)
+    const uint32_t t = d * qc.mul + qc.add;           // lanes: (d + e) * k + c  < 2^16
+    // r = t >> shift per lane, q = r * scale -- done as one high multiply on the masked quotient bits, which
+    // moves the shift off the ALU pipe: ((r << n) * (scale << (32 - n))) >> 32 == r * scale in both lanes
+    uint32_t q = __umulhi(t & qc.rmask, qc.qmul);     // :54 table[d]
+    const uint32_t ov = q + p;                        // bit 8 = overflow                      (:56)
     // overflow_is_expected = [a < p] = !bit8(dd)  =>  mismatch iff bit8(ov) == bit8(dd)       (:57-58)
     const uint32_t x = ~(ov ^ dd) & 0x01000100u;
-    const uint32_t m = x - (x >> 8);                  // 0x00FF in every mismatching lane
+    const uint32_t m = __umulhi(x, 0xFF000000u);      // (x * 255) >> 8: 0x00FF in every mismatching lane
     q = (q & ~m) | (d & m);                           // :59
     recon = ((ov & ~m) | (a & m)) & M16;              // :63 (p + q) mod 256, == a after a fix-up
     return q;
@@ -263,7 +273,7 @@ __device__ __forceinline__ void coarse_level(FastSmem& sm, int tid, const QuantS
 }
 
 #ifndef HGI_FAST_MIN_BLOCKS
-#define HGI_FAST_MIN_BLOCKS 8
+#define HGI_FAST_MIN_BLOCKS 6
 #endif
 
 template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV>
@@ -285,31 +295,38 @@ hgi_tile_fast_kernel(const PassArgs p)
     const bool top = (p.c_recon == nullptr);
     const QuantSwar qc = quant_swar(p.quant_error);
 
-    // ---- 1. global loads: this thread's 16x2 pixels (kept in registers for the finest level) ----
-    const int sx = tid & 7, ry = tid >> 3;          // 8 column strips x 32 row pairs
+    // ---- 1. global loads: this thread's NU 16x2-pixel units (kept in registers for the finest level) ----
+    const int sx = tid & 7, ry = tid >> 3;          // 8 column strips x 32 row pairs (x NU units, 64 rows apart)
     const bool col_ok = 16 * sx < xin;
-    const bool row0_ok = 2 * ry < yin, row1_ok = 2 * ry + 1 < yin;
     const uint32_t toff = (uint32_t)(2 * ry) * p.w + (uint32_t)(16 * sx);   // tile-relative, fits 32 bits
-    uint4 ev = make_uint4(0u, 0u, 0u, 0u), od = make_uint4(0u, 0u, 0u, 0u);
-    if (col_ok && row0_ok) ev = __ldg(reinterpret_cast<const uint4*>(tile + toff));
-    if (col_ok && row1_ok) od = __ldg(reinterpret_cast<const uint4*>(tile + toff + p.w));
+    uint4 ev[NU], od[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+        ev[u] = make_uint4(0u, 0u, 0u, 0u);
+        od[u] = make_uint4(0u, 0u, 0u, 0u);
+        const int y = 2 * ry + 64 * u;
+        if (col_ok && y < yin) ev[u] = __ldg(reinterpret_cast<const uint4*>(tile + toff + (uint32_t)(64 * u) * p.w));
+        if (col_ok && y + 1 < yin) od[u] = __ldg(reinterpret_cast<const uint4*>(tile + toff + (uint32_t)(64 * u + 1) * p.w));
+    }
 
-    // halo chunks (right of / below the tile) feed only the coarse planes; the last two warps fetch
-    // them: 32 right-halo chunks (rows 0,2,..,TH-2; column TW) + rows TH, TH+4, TH+8 (chunks 0..8)
-    const int hj = tid - (NT - 64);
+    // halo chunks (right of / below the tile) feed only the coarse planes; the upper half of the CTA
+    // fetches them: TH/2 right-halo chunks (rows 0,2,..,TH-2; column TW) + rows TH, TH+4, TH+8 (chunks 0..8)
+    constexpr int NRIGHT = TH / 2, NHALO = NRIGHT + 27;
+    const int hj = tid - (NT - 128);
     int hy = 2 * hj, hc = 8;
-    if (hj >= 32) {
-        const int r = (hj - 32) / 9;
-        hc = (hj - 32) - 9 * r;
+    if (hj >= NRIGHT) {
+        const int r = (hj - NRIGHT) / 9;
+        hc = (hj - NRIGHT) - 9 * r;
         hy = TH + 4 * r;
     }
-    const bool halo = NLEV > 1 && hj >= 0 && hj < 59;
+    const bool halo = NLEV > 1 && hj >= 0 && hj < NHALO;
     uint4 hv = make_uint4(0u, 0u, 0u, 0u);
     if (halo && hy < yin && 16 * hc < xin)
         hv = __ldg(reinterpret_cast<const uint4*>(tile + (uint32_t)hy * p.w + (uint32_t)(16 * hc)));
 
     // ---- 2. stage the dense coarse planes + the coarse lattice of this pass ---------------------
-    stage_chunk<F>(sm.P, ev, 2 * ry, sx);
+#pragma unroll
+    for (int u = 0; u < NU; ++u) stage_chunk<F>(sm.P, ev[u], 2 * ry + 64 * u, sx);
     if (halo) stage_chunk<F>(sm.P, hv, hy, hc);
     {
         constexpr int ncx = TW / F + 2, ncy = TH / F + 2;
@@ -342,59 +359,64 @@ hgi_tile_fast_kernel(const PassArgs p)
     if (F >= 4) coarse_level<MODE, INTERP, IDENTITY, 2>(sm, tid, qc, edge, xin, yin);
 
     // ---- 4. finest level: registers + P_2 / Q_2 -> HBM -------------------------------------------
-    const uint8_t* P2r = sm.P + plane_off(2) + ry * plane_pitch(2) + 8 * sx;
-    const uint2 ctw = *reinterpret_cast<const uint2*>(P2r);
-    const uint2 cbw = *reinterpret_cast<const uint2*>(P2r + plane_pitch(2));
-    const uint32_t cte = P2r[8], cbe = P2r[plane_pitch(2) + 8];
-    uint32_t A[4], B[4], C[4], D[4];
-    A[0] = lanes01(ctw.x); A[1] = lanes23(ctw.x); A[2] = lanes01(ctw.y); A[3] = lanes23(ctw.y);
-    B[0] = lanes01(cbw.x); B[1] = lanes23(cbw.x); B[2] = lanes01(cbw.y); B[3] = lanes23(cbw.y);
-    C[0] = lanes12(ctw.x); C[1] = __funnelshift_r(A[1], A[2], 16); C[2] = lanes12(ctw.y); C[3] = __funnelshift_r(A[3], cte, 16);
-    D[0] = lanes12(cbw.x); D[1] = __funnelshift_r(B[1], B[2], 16); D[2] = lanes12(cbw.y); D[3] = __funnelshift_r(B[3], cbe, 16);
-    const uint32_t evw[4] = {ev.x, ev.y, ev.z, ev.w};
-    const uint32_t odw[4] = {od.x, od.y, od.z, od.w};
-    uint32_t out_ev[4], out_od[4], rec_ev[4], rec_od[4];
-    uint2 qcw = make_uint2(0u, 0u);
-    if (MODE == kModeEncode) qcw = *reinterpret_cast<const uint2*>(sm.Q + plane_off(2) + ry * plane_pitch(2) + 8 * sx);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t pr = pred2<INTERP>(A[k], B[k], C[k], D[k]);
-        const uint32_t a1 = lanes_odd(evw[k]), a2 = lanes_even(odw[k]), a3 = lanes_odd(odw[k]);
-        if (MODE == kModeEncode) {
-            uint32_t r1, r2, r3;
-            const uint32_t pk = 0x01000100u - pr;
-            const uint32_t q1 = encode2<IDENTITY>(a1, pr, pk, qc, r1);
-            const uint32_t q2 = encode2<IDENTITY>(a2, pr, pk, qc, r2);
-            const uint32_t q3 = encode2<IDENTITY>(a3, pr, pk, qc, r3);
-            const uint32_t qw = (k < 2) ? qcw.x : qcw.y;
-            const uint32_t QA = (k & 1) ? lanes23(qw) : lanes01(qw);
-            out_ev[k] = interleave(QA, q1);
-            out_od[k] = interleave(q2, q3);
-            if (EXTRA) {
-                rec_ev[k] = interleave(A[k], r1);
-                rec_od[k] = interleave(r2, r3);
-            }
-        } else {
-            out_ev[k] = interleave(A[k], decode2(a1, pr));
-            out_od[k] = interleave(decode2(a2, pr), decode2(a3, pr));
-        }
-    }
     uint8_t* __restrict__ out = (MODE == kModeEncode ? p.grid_out : p.recon_out) + tile_off;
-    if (col_ok && row0_ok) *reinterpret_cast<uint4*>(out + toff) = make_uint4(out_ev[0], out_ev[1], out_ev[2], out_ev[3]);
-    if (col_ok && row1_ok) *reinterpret_cast<uint4*>(out + toff + p.w) = make_uint4(out_od[0], out_od[1], out_od[2], out_od[3]);
-    if (MODE == kModeEncode && EXTRA) {
-        if (p.recon_out != nullptr) {
-            uint8_t* __restrict__ rout = p.recon_out + tile_off;
-            if (col_ok && row0_ok) *reinterpret_cast<uint4*>(rout + toff) = make_uint4(rec_ev[0], rec_ev[1], rec_ev[2], rec_ev[3]);
-            if (col_ok && row1_ok) *reinterpret_cast<uint4*>(rout + toff + p.w) = make_uint4(rec_od[0], rec_od[1], rec_od[2], rec_od[3]);
+    if (MODE == kModeEncode && EXTRA && p.hist != nullptr) {
+        for (int i = tid; i < NWARPS * 256; i += NT) whist[i] = 0u;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+        const int rp = ry + 32 * u;                 // row pair (cell row) of this unit
+        const bool row0_ok = 2 * rp < yin, row1_ok = 2 * rp + 1 < yin;
+        const uint32_t uoff = toff + (uint32_t)(64 * u) * p.w;
+        const uint8_t* P2r = sm.P + plane_off(2) + rp * plane_pitch(2) + 8 * sx;
+        const uint2 ctw = *reinterpret_cast<const uint2*>(P2r);
+        const uint2 cbw = *reinterpret_cast<const uint2*>(P2r + plane_pitch(2));
+        const uint32_t cte = P2r[8], cbe = P2r[plane_pitch(2) + 8];
+        uint32_t A[4], B[4], C[4], D[4];
+        A[0] = lanes01(ctw.x); A[1] = lanes23(ctw.x); A[2] = lanes01(ctw.y); A[3] = lanes23(ctw.y);
+        B[0] = lanes01(cbw.x); B[1] = lanes23(cbw.x); B[2] = lanes01(cbw.y); B[3] = lanes23(cbw.y);
+        C[0] = lanes12(ctw.x); C[1] = __funnelshift_r(A[1], A[2], 16); C[2] = lanes12(ctw.y); C[3] = __funnelshift_r(A[3], cte, 16);
+        D[0] = lanes12(cbw.x); D[1] = __funnelshift_r(B[1], B[2], 16); D[2] = lanes12(cbw.y); D[3] = __funnelshift_r(B[3], cbe, 16);
+        const uint32_t evw[4] = {ev[u].x, ev[u].y, ev[u].z, ev[u].w};
+        const uint32_t odw[4] = {od[u].x, od[u].y, od[u].z, od[u].w};
+        uint32_t out_ev[4], out_od[4], rec_ev[4], rec_od[4];
+        uint2 qcw = make_uint2(0u, 0u);
+        if (MODE == kModeEncode) qcw = *reinterpret_cast<const uint2*>(sm.Q + plane_off(2) + rp * plane_pitch(2) + 8 * sx);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t pr = pred2<INTERP>(A[k], B[k], C[k], D[k]);
+            const uint32_t a1 = lanes_odd(evw[k]), a2 = lanes_even(odw[k]), a3 = lanes_odd(odw[k]);
+            if (MODE == kModeEncode) {
+                uint32_t r1, r2, r3;
+                const uint32_t pk = 0x01000100u - pr;
+                const uint32_t q1 = encode2<IDENTITY>(a1, pr, pk, qc, r1);
+                const uint32_t q2 = encode2<IDENTITY>(a2, pr, pk, qc, r2);
+                const uint32_t q3 = encode2<IDENTITY>(a3, pr, pk, qc, r3);
+                const uint32_t qw = (k < 2) ? qcw.x : qcw.y;
+                const uint32_t QA = (k & 1) ? lanes23(qw) : lanes01(qw);
+                out_ev[k] = interleave(QA, q1);
+                out_od[k] = interleave(q2, q3);
+                if (EXTRA) {
+                    rec_ev[k] = interleave(A[k], r1);
+                    rec_od[k] = interleave(r2, r3);
+                }
+            } else {
+                out_ev[k] = interleave(A[k], decode2(a1, pr));
+                out_od[k] = interleave(decode2(a2, pr), decode2(a3, pr));
+            }
         }
-        // residual histogram (north_star's archive.rs stage): warp-private bins, one global atomic per
-        // non-empty bin per tile
-        if (p.hist != nullptr) {
-            for (int i = tid; i < NWARPS * 256; i += NT) whist[i] = 0u;
-            __syncthreads();
-            uint32_t* mine = &whist[(tid >> 5) * 256];
-            if (col_ok) {
+        if (col_ok && row0_ok) *reinterpret_cast<uint4*>(out + uoff) = make_uint4(out_ev[0], out_ev[1], out_ev[2], out_ev[3]);
+        if (col_ok && row1_ok) *reinterpret_cast<uint4*>(out + uoff + p.w) = make_uint4(out_od[0], out_od[1], out_od[2], out_od[3]);
+        if (MODE == kModeEncode && EXTRA) {
+            if (p.recon_out != nullptr) {
+                uint8_t* __restrict__ rout = p.recon_out + tile_off;
+                if (col_ok && row0_ok) *reinterpret_cast<uint4*>(rout + uoff) = make_uint4(rec_ev[0], rec_ev[1], rec_ev[2], rec_ev[3]);
+                if (col_ok && row1_ok) *reinterpret_cast<uint4*>(rout + uoff + p.w) = make_uint4(rec_od[0], rec_od[1], rec_od[2], rec_od[3]);
+            }
+            // residual histogram (north_star's archive.rs stage): warp-private shared-memory bins
+            if (p.hist != nullptr && col_ok) {
+                uint32_t* mine = &whist[(tid >> 5) * 256];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
 #pragma unroll
@@ -404,20 +426,23 @@ hgi_tile_fast_kernel(const PassArgs p)
                     }
                 }
             }
-            __syncthreads();
-            uint32_t total = 0;
-#pragma unroll
-            for (int wv = 0; wv < NWARPS; ++wv) total += whist[wv * 256 + tid];
-            if (total) atomicAdd(&p.hist[(size_t)img * 256 + tid], total);
         }
+    }
+    if (MODE == kModeEncode && EXTRA && p.hist != nullptr) {   // one global atomic per non-empty bin per tile
+        __syncthreads();
+        uint32_t total = 0;
+#pragma unroll
+        for (int wv = 0; wv < NWARPS; ++wv) total += whist[wv * 256 + tid];
+        if (total) atomicAdd(&p.hist[(size_t)img * 256 + tid], total);
     }
 }
 
 template <int MODE, int INTERP, int NLEV>
 cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
 {
-    if (args.tiles_x == 0 || args.tiles_y == 0 || args.n_images == 0) return cudaSuccess;
-    if (args.tiles_y > 65535u) return cudaErrorInvalidConfiguration;
+    const uint32_t tiles_x = (args.w + TW - 1) / TW, tiles_y = (args.h + TH - 1) / TH;
+    if (tiles_x == 0 || tiles_y == 0 || args.n_images == 0) return cudaSuccess;
+    if (tiles_y > 65535u) return cudaErrorInvalidConfiguration;
     const size_t plane = (size_t)args.w * args.h;
     for (uint32_t first = 0; first < args.n_images; first += 65535u) {   // gridDim.z limit
         PassArgs a = args;
@@ -428,7 +453,7 @@ cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
         if (args.hist) a.hist = args.hist + (size_t)first * 256;
         if (args.c_recon) a.c_recon = args.c_recon + (size_t)first * args.cw * args.ch;
         if (args.c_q) a.c_q = args.c_q + (size_t)first * args.cw * args.ch;
-        const dim3 nb(a.tiles_x, a.tiles_y, a.n_images);
+        const dim3 nb(tiles_x, tiles_y, a.n_images);
         if (MODE == kModeDecode) {
             hgi_tile_fast_kernel<kModeDecode, INTERP, true, false, NLEV><<<nb, NT, 0, stream>>>(a);
         } else {
@@ -469,8 +494,7 @@ bool quant_swar_self_check()
             const uint32_t d1 = 255u - d0;
             const uint32_t d = d0 | (d1 << 16);
             const uint32_t t = d * q.mul + q.add;
-            const uint32_t r = (t >> q.shift) & 0x000F000Fu;
-            const uint32_t v = r * q.scale;
+            const uint32_t v = (uint32_t)(((unsigned long long)(t & q.rmask) * q.qmul) >> 32);
             if ((v & 0xFFFFu) != quant_entry(d0, e) || (v >> 16) != quant_entry(d1, e)) return false;
         }
     }

@@ -17,11 +17,10 @@ def ref_pred(A, B, C, D):
 
 
 def swar_pred(A, B, C, D):                                    # pred2<Crossed>
-    x1 = A ^ B
-    t1 = x1 | (C ^ D)
-    t2 = (~(x1 ^ C ^ D) & U32) & (A ^ C)
-    s = (A + B + C) + (D + (t1 & 0x00010001) + (t2 & 0x00010001))
-    return (s >> 2) & M16
+    x1 = (A ^ B) & 0x00010001
+    w = x1 & (C ^ D) & (A ^ C)
+    h = ((A + B + C) + (D + 0x00010001)) >> 1
+    return ((h + w) >> 1) & M16
 
 
 def test_parity_predictor_all_low_bit_patterns_and_ranges():
@@ -47,11 +46,11 @@ def swar_encode2(a, p, error):
     dd = (a + pk) & U32
     d = dd & M16
     t = (d * k + add) & U32
-    r = (t >> n) & 0x000F000F
-    q = (r * scale) & U32
-    ov = (r * scale + p) & U32
+    rmask = ((0xF << n) * 0x00010001) & U32
+    q = ((t & rmask) * (scale << (32 - n))) >> 32             # __umulhi
+    ov = (q + p) & U32
     x = (~(ov ^ dd)) & 0x01000100
-    m = (x - (x >> 8)) & U32
+    m = (x * 0xFF000000) >> 32                                # __umulhi: 0x00FF per mismatching lane
     q = (q & ~m & U32) | (d & m)
     recon = ((ov & ~m) | (a & m)) & M16
     return q, recon
@@ -85,3 +84,4 @@ def test_swar_quantizer_constants_are_exact():
         for d in range(256):
             t = d * k + error * k + c
             assert t < 65536 and ((t >> n) & 15) * scale == ((d + error) // scale) * scale
+            assert ((t & (0xF << n)) * (scale << (32 - n))) >> 32 == ((d + error) // scale) * scale
