@@ -138,6 +138,11 @@ int hgi_histogram_u8(hgi_ctx_t *ctx, const uint8_t *grid, size_t n, uint64_t his
 int hgi_error_metrics_u8(hgi_ctx_t *ctx, const uint8_t *before, const uint8_t *after, size_t n,
                          uint64_t *sum_sq_out, uint64_t *sd_int_out, uint32_t *max_abs_out);
 
+/* RGB8 (interleaved r,g,b) -> luma, the `to_luma()` of the `image` 0.19 crate that src/main.rs:42,74
+   applies before encoding: l = 0.2126f*r + 0.7152f*g + 0.0722f*b in f32, left to right, every
+   multiply and add rounded separately (no FMA), truncated to u8. */
+int hgi_rgb_to_luma_u8(hgi_ctx_t *ctx, const uint8_t *rgb, size_t n_pixels, uint8_t *luma_out);
+
 /* ---- device-pointer entry points (the timed ones) -------------------------------------- */
 int hgi_encode_dev(hgi_ctx_t *ctx, const uint8_t *d_images, uint32_t n_images, uint32_t width,
                    uint32_t height, const hgi_params_t *params, uint8_t *d_grids_out,
@@ -147,6 +152,8 @@ int hgi_encode_dev(hgi_ctx_t *ctx, const uint8_t *d_images, uint32_t n_images, u
 int hgi_decode_dev(hgi_ctx_t *ctx, const uint8_t *d_grids, uint32_t n_images, uint32_t width,
                    uint32_t height, const hgi_params_t *params, uint8_t *d_images_out,
                    void *stream);
+int hgi_rgb_to_luma_dev(hgi_ctx_t *ctx, const uint8_t *d_rgb, size_t n_pixels, uint8_t *d_luma_out,
+                        void *stream);
 int hgi_histogram_dev(hgi_ctx_t *ctx, const uint8_t *d_grid, size_t n_per_image,
                       uint32_t n_images, uint32_t *d_hist_out /* [n_images][256], overwritten */,
                       void *stream);

@@ -51,6 +51,8 @@ PROTOTYPES = {
     "hgi_decode_batch_u8": (_int, [_vp, _vp, _u32, _u32, _u32, _pp, _vp]),
     "hgi_histogram_u8": (_int, [_vp, _vp, _sz, _vp]),
     "hgi_error_metrics_u8": (_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "hgi_rgb_to_luma_u8": (_int, [_vp, _vp, _sz, _vp]),
+    "hgi_rgb_to_luma_dev": (_int, [_vp, _vp, _sz, _vp, _vp]),
     "hgi_encode_dev": (_int, [_vp, _vp, _u32, _u32, _u32, _pp, _vp, _vp, _vp, _vp]),
     "hgi_decode_dev": (_int, [_vp, _vp, _u32, _u32, _u32, _pp, _vp, _vp]),
     "hgi_histogram_dev": (_int, [_vp, _vp, _sz, _u32, _vp, _vp]),

@@ -314,6 +314,18 @@ def error_metrics(before, after, ctx=None):
     return {"sum_sq": s.value, "sd_int": q.value, "max_abs": m.value, "sd": float(q.value) ** 0.5}
 
 
+def rgb_to_luma(rgb, ctx=None):
+    """`image::DynamicImage::to_luma()` as called at src/main.rs:42,74 (f32 weights, no FMA, truncation).
+    `rgb` is (h, w, 3) uint8; returns the (h, w) luma plane the codec consumes."""
+    ctx = ctx or Context.default()
+    a = np.ascontiguousarray(rgb, dtype=np.uint8)
+    if a.ndim != 3 or a.shape[2] != 3:
+        raise ValueError("rgb must be (h, w, 3)")
+    out = np.empty(a.shape[:2], np.uint8)
+    ctx.check(_lib.lib().hgi_rgb_to_luma_u8(ctx._h, a.ctypes.data, out.size, out.ctypes.data), "hgi_rgb_to_luma_u8")
+    return out
+
+
 class Metadata:
     """src/archive.rs:15-22."""
 

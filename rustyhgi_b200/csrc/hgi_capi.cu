@@ -508,6 +508,43 @@ int hgi_error_metrics_dev(hgi_ctx_t* ctx, const uint8_t* d_before, const uint8_t
     return HGI_OK;
 }
 
+int hgi_rgb_to_luma_dev(hgi_ctx_t* ctx, const uint8_t* d_rgb, size_t n_pixels, uint8_t* d_luma_out, void* stream)
+{
+    if (!ctx) return HGI_ERR_INVALID_ARG;
+    if (n_pixels == 0) return HGI_OK;
+    if (!d_rgb || !d_luma_out || n_pixels > ((size_t)1 << 60)) return HGI_ERR_INVALID_ARG;
+    DeviceGuard g(ctx);
+    if (!g.ok) return HGI_ERR_CUDA;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    HGI_CUDA(ctx, hgi::launch_rgb_to_luma(d_rgb, n_pixels, d_luma_out, st));
+    ctx->launches++;
+    return HGI_OK;
+}
+
+int hgi_rgb_to_luma_u8(hgi_ctx_t* ctx, const uint8_t* rgb, size_t n_pixels, uint8_t* luma_out)
+{
+    if (!ctx) return HGI_ERR_INVALID_ARG;
+    if (n_pixels == 0) return HGI_OK;
+    if (!rgb || !luma_out || n_pixels > ((size_t)1 << 60)) return HGI_ERR_INVALID_ARG;
+    DeviceGuard g(ctx);
+    if (!g.ok) return HGI_ERR_CUDA;
+    Slot& sl = ctx->slots[0];
+    if (!sl.stream) HGI_CUDA(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    const size_t chunk = (size_t)64 << 20;   // pixels per chunk
+    int rc = reserve(ctx, sl.in, 3 * (n_pixels < chunk ? n_pixels : chunk));
+    if (!rc) rc = reserve(ctx, sl.out, n_pixels < chunk ? n_pixels : chunk);
+    if (rc) return rc;
+    for (size_t off = 0; off < n_pixels; off += chunk) {
+        const size_t len = (n_pixels - off < chunk) ? n_pixels - off : chunk;
+        HGI_CUDA(ctx, cudaMemcpyAsync(sl.in.p, rgb + 3 * off, 3 * len, cudaMemcpyHostToDevice, sl.stream));
+        HGI_CUDA(ctx, hgi::launch_rgb_to_luma(sl.in.p, len, sl.out.p, sl.stream));
+        ctx->launches++;
+        HGI_CUDA(ctx, cudaMemcpyAsync(luma_out + off, sl.out.p, len, cudaMemcpyDeviceToHost, sl.stream));
+        HGI_CUDA(ctx, cudaStreamSynchronize(sl.stream));
+    }
+    return HGI_OK;
+}
+
 int hgi_encode_batch_u8(hgi_ctx_t* ctx, const uint8_t* images, uint32_t n_images, uint32_t width, uint32_t height,
                         const hgi_params_t* params, uint8_t* grids_out, uint32_t* hist_out)
 {

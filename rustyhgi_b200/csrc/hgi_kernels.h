@@ -58,6 +58,7 @@ cudaError_t launch_level(int mode, int interp, const LevelArgs& args, cudaStream
 // ---- reductions ---------------------------------------------------------------------------
 cudaError_t launch_histogram(const uint8_t* data, size_t n_per_image, uint32_t n_images,
                              uint32_t* hist_out, cudaStream_t stream);
+cudaError_t launch_rgb_to_luma(const uint8_t* rgb, size_t n_pixels, uint8_t* luma, cudaStream_t stream);
 cudaError_t launch_error_metrics(const uint8_t* before, const uint8_t* after, size_t n,
                                  unsigned long long* out2, cudaStream_t stream);
 

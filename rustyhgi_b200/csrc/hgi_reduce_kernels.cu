@@ -87,7 +87,60 @@ hgi_error_kernel(const uint8_t* __restrict__ before, const uint8_t* __restrict__
     }
 }
 
+// RGB -> luma, the `image` 0.19 `to_luma()` that src/main.rs:42,74 calls before encoding:
+// l = 0.2126f*r + 0.7152f*g + 0.0722f*b in f32, evaluated left to right with separately rounded
+// multiplies and adds (Rust never contracts to FMA), truncated to u8.  __fmul_rn/__fadd_rn are never
+// fused by nvcc, independent of -fmad.
+__device__ __forceinline__ uint32_t luma_of(uint32_t r, uint32_t g, uint32_t b)
+{
+    float l = __fmul_rn(0.2126f, (float)r);
+    l = __fadd_rn(l, __fmul_rn(0.7152f, (float)g));
+    l = __fadd_rn(l, __fmul_rn(0.0722f, (float)b));
+    return (uint32_t)l;   // truncation; l < 256
+}
+
+// 16 pixels per thread: three 128-bit loads (48 RGB bytes), one 128-bit store.
+__global__ void __launch_bounds__(256)
+hgi_luma_kernel(const uint8_t* __restrict__ rgb, size_t n_pixels, uint8_t* __restrict__ luma, int vec_ok)
+{
+    const size_t groups = n_pixels / 16;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec_ok) {
+        for (size_t gidx = tid; gidx < groups; gidx += stride) {
+            const uint4* src = reinterpret_cast<const uint4*>(rgb + gidx * 48);
+            const uint4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2);
+            const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+            uint32_t out[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {   // 4 pixels = 12 bytes = words 3q..3q+2
+                const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
+                const uint32_t l0 = luma_of(a & 255u, (a >> 8) & 255u, (a >> 16) & 255u);
+                const uint32_t l1 = luma_of(a >> 24, b & 255u, (b >> 8) & 255u);
+                const uint32_t l2 = luma_of((b >> 16) & 255u, b >> 24, c & 255u);
+                const uint32_t l3 = luma_of((c >> 8) & 255u, (c >> 16) & 255u, c >> 24);
+                out[q] = l0 | (l1 << 8) | (l2 << 16) | (l3 << 24);
+            }
+            *reinterpret_cast<uint4*>(luma + gidx * 16) = make_uint4(out[0], out[1], out[2], out[3]);
+        }
+    }
+    const size_t first = vec_ok ? groups * 16 : 0;
+    for (size_t i = first + tid; i < n_pixels; i += stride)
+        luma[i] = (uint8_t)luma_of(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+}
+
 }  // namespace
+
+cudaError_t launch_rgb_to_luma(const uint8_t* rgb, size_t n_pixels, uint8_t* luma, cudaStream_t stream)
+{
+    if (n_pixels == 0) return cudaSuccess;
+    const int vec_ok = (((uintptr_t)rgb | (uintptr_t)luma) & 15u) == 0;
+    uint64_t blocks = (n_pixels / 16 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    hgi_luma_kernel<<<(uint32_t)blocks, 256, 0, stream>>>(rgb, n_pixels, luma, vec_ok);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_histogram(const uint8_t* data, size_t n_per_image, uint32_t n_images,
                              uint32_t* hist_out, cudaStream_t stream)

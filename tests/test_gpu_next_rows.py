@@ -1,0 +1,74 @@
+"""SURVEY.md 8(f) "next" rows on the GPU: f-2 RGB->luma, f-3 `hgi test` metrics, f-4 the CLI shell."""
+import io
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import rustyhgi_b200 as hgi
+from conftest import GOLDEN, load_plane, sha16
+from oracle import c as oc
+from rustyhgi_b200 import cli
+
+pytestmark = pytest.mark.gpu
+
+
+def test_rgb_to_luma_exhaustive_all_16m_triples():
+    """Every (r,g,b) in 2^24 against the CPU restatement of image-0.19's f32 formula (no FMA)."""
+    v = np.arange(1 << 24, dtype=np.uint32)
+    rgb = np.stack([(v >> 16) & 255, (v >> 8) & 255, v & 255], axis=1).astype(np.uint8).reshape(4096, 4096, 3)
+    got = hgi.rgb_to_luma(rgb)
+    want = oc.rgb_to_luma(rgb)
+    assert int((got != want).sum()) == 0
+    gray = np.repeat(np.arange(256, dtype=np.uint8), 3).reshape(1, 256, 3)      # f32 sum lands on v-1 for some v
+    assert (hgi.rgb_to_luma(gray) == oc.rgb_to_luma(gray)).all()
+
+
+def test_rgb_to_luma_ragged_and_unaligned():
+    rng = np.random.default_rng(2)
+    for h, w in ((1, 1), (3, 5), (7, 16), (33, 31), (250, 243)):
+        rgb = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+        assert (hgi.rgb_to_luma(rgb) == oc.rgb_to_luma(rgb)).all()
+
+
+def test_docs_source_image_luma_matches_golden():
+    """The palette PNG of the docs pair goes RGB -> luma on the GPU and must equal the golden plane."""
+    from PIL import Image
+    rgb = np.array(Image.open(os.path.join(GOLDEN, "docs_lena_source.png")).convert("RGB"))
+    # the fixture is already luma (gray triples): to_luma of gray input lands on v or v-1
+    assert (hgi.rgb_to_luma(rgb) == oc.rgb_to_luma(rgb)).all()
+
+
+def test_cli_test_subcommand_config1(tmp_path, monkeypatch, capsys):
+    """BASELINE config 1: `hgi test res/LENA.TIF` (level 4, Medium) -> `Uncompressed: 64 kb`, `SD: 9.17`."""
+    monkeypatch.chdir(tmp_path)
+    src = os.path.join(GOLDEN, "lena_tif.png")
+    cli.main(["test", src, "-l", "4", "-q", "Medium", "-s", "_hgi"])
+    out = capsys.readouterr().out.splitlines()
+    assert out[0] == "Uncompressed: 64 kb"
+    assert out[3] == "SD:           9.17"
+    assert out[1].startswith("Compressed:   ") and out[2].startswith("Ratio:        ")
+    from PIL import Image
+    after = np.array(Image.open(tmp_path / "lena_tif_hgi.png"))
+    assert sha16(after) == "e17f5ad9f400234e"
+    raw = (tmp_path / "lena_tif_hgi.hgi").read_bytes()
+    assert raw[:4] == bytes.fromhex("55a5adba")
+    payload = zlib.decompress(raw[28:], -15)
+    assert sha16(np.frombuffer(payload[8:-8], np.uint8)) == "3a992020370c96a4"
+
+
+def test_cli_encode_decode_roundtrip(tmp_path):
+    src = os.path.join(GOLDEN, "lena_tif.png")
+    arch, png = str(tmp_path / "a.hgi"), str(tmp_path / "a.png")
+    cli.main(["encode", "-i", src, "-o", arch, "-q", "low"])            # default level 4 (src/options.rs:55)
+    cli.main(["decode", "-i", arch, "-o", png])
+    from PIL import Image
+    got = np.array(Image.open(png))
+    want = oc.decode(oc.encode(load_plane("lena_tif"), 4, qlevel=oc.LOW), 4)
+    assert (got == want).all()
+
+
+def test_cli_swallows_errors_like_reference(tmp_path, capsys):
+    cli.main(["decode", "-i", str(tmp_path / "missing.hgi"), "-o", str(tmp_path / "x.png")])
+    assert "An error occured" in capsys.readouterr().err               # src/main.rs:130-134
