@@ -68,11 +68,12 @@ typedef enum {
     HGI_QLEVEL_HIGH = 3
 } hgi_quant_level_t;
 
-/* Which CUDA path a context uses.  Both produce identical bytes. */
+/* Which CUDA path a context uses.  All produce identical bytes. */
 typedef enum {
-    HGI_PATH_TILE = 0,      /* default: fused multi-level shared-memory tile kernels */
-    HGI_PATH_PER_LEVEL = 1, /* one kernel per level over HBM (north_star's literal shape) */
-    HGI_PATH_TILE_GENERIC = 2 /* fused tiles, but always the generic (scalar, any alignment) kernel */
+    HGI_PATH_TILE = 0,         /* default: fused multi-level tile kernels (register-prefetch SWAR kernel where eligible) */
+    HGI_PATH_PER_LEVEL = 1,    /* one kernel per level over HBM (north_star's literal shape) */
+    HGI_PATH_TILE_GENERIC = 2, /* fused tiles, always the generic (scalar, any alignment) kernel */
+    HGI_PATH_TILE_TMA = 3      /* fused tiles, persistent TMA-pipelined SWAR kernel instead of the prefetch one */
 } hgi_path_t;
 
 #define HGI_MAX_LEVELS 31u

@@ -41,7 +41,7 @@ class InterpolationType(enum.IntEnum):      # src/interpolator.rs:4-9 (serialisa
 
 _INTERP_LEFTTOP = 3
 _QUANT_NOOP, _QUANT_LINEAR = 0, 1
-PATH_TILE, PATH_PER_LEVEL, PATH_TILE_GENERIC = 0, 1, 2
+PATH_TILE, PATH_PER_LEVEL, PATH_TILE_GENERIC, PATH_TILE_TMA = 0, 1, 2, 3
 
 
 class Crossed:                              # src/interpolator.rs:30

@@ -194,7 +194,9 @@ int run_tile_path(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images,
             a.s_recon = ctx->compact[set].p;
             a.s_q = ctx->compact[set + 1].p;
         }
-        HGI_CUDA(ctx, hgi::launch_tile_pass(mode, prm->interp, a, st, ctx->path == HGI_PATH_TILE_GENERIC));
+        const int variant = ctx->path == HGI_PATH_TILE_GENERIC ? hgi::kTileGeneric
+                            : (ctx->path == HGI_PATH_TILE_TMA ? hgi::kTileTma : hgi::kTileAuto);
+        HGI_CUDA(ctx, hgi::launch_tile_pass(mode, prm->interp, a, st, variant));
         ctx->launches++;
         c_recon = a.s_recon;
         c_q = a.s_q;
@@ -269,7 +271,7 @@ int run_dev(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images, uint3
         HGI_CUDA(ctx, cudaMemcpyAsync(primary, src, (size_t)n_images * plane, cudaMemcpyDeviceToDevice, st));
         if (mode == hgi::kModeEncode && recon_out)
             HGI_CUDA(ctx, cudaMemcpyAsync(recon_out, src, (size_t)n_images * plane, cudaMemcpyDeviceToDevice, st));
-    } else if (ctx->path == HGI_PATH_PER_LEVEL) {
+    } else if (ctx->path == HGI_PATH_PER_LEVEL) {  // all other paths are tile variants
         int rc = run_level_path(ctx, mode, src, n_images, w, h, levels, prm, grid_out, recon_out, st);
         if (rc) return rc;
     } else {
@@ -414,7 +416,7 @@ void hgi_ctx_destroy(hgi_ctx_t* ctx)
 
 int hgi_ctx_set_path(hgi_ctx_t* ctx, int path)
 {
-    if (!ctx || path < HGI_PATH_TILE || path > HGI_PATH_TILE_GENERIC) return HGI_ERR_INVALID_ARG;
+    if (!ctx || path < HGI_PATH_TILE || path > HGI_PATH_TILE_TMA) return HGI_ERR_INVALID_ARG;
     ctx->path = path;
     return HGI_OK;
 }

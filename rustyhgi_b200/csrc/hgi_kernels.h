@@ -34,11 +34,14 @@ struct PassArgs {
     uint32_t vec_ok;         // D==1 and rows are 16-byte aligned => 128-bit global accesses
 };
 
-// Dispatches to the fast kernel (hgi_tile_fast.cu) for D == 1 passes on 16-byte-aligned planes and
-// to the generic kernel (hgi_tile_kernels.cu) otherwise.  `force_generic` is a test hook.
-cudaError_t launch_tile_pass(int mode, int interp, const PassArgs& args, cudaStream_t stream,
-                             bool force_generic = false);
+// Dispatch of one pass.  kTileAuto: D == 1 passes on 16-byte-aligned planes go to the register-prefetch SWAR
+// kernel (hgi_tile_fast.cu), everything else to the generic kernel (hgi_tile_kernels.cu).  kTileTma selects
+// the persistent TMA-pipelined kernel (hgi_tile_tma.cu) for the eligible passes instead -- measured slower
+// than the prefetch kernel in round 1 (profiles/), kept as a tested alternative.
+enum TileVariant : int { kTileAuto = 0, kTileGeneric = 1, kTileTma = 2 };
+cudaError_t launch_tile_pass(int mode, int interp, const PassArgs& args, cudaStream_t stream, int variant = kTileAuto);
 cudaError_t launch_tile_pass_fast(int mode, int interp, const PassArgs& args, cudaStream_t stream);
+cudaError_t launch_tile_pass_tma(int mode, int interp, const PassArgs& args, cudaStream_t stream, bool* used);
 bool quant_swar_self_check();
 
 // ---- per-level path -----------------------------------------------------------------------

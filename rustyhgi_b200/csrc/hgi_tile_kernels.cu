@@ -231,9 +231,16 @@ cudaError_t launch_t(const PassArgs& a, cudaStream_t stream)
 
 }  // namespace
 
-cudaError_t launch_tile_pass(int mode, int interp, const PassArgs& a, cudaStream_t stream, bool force_generic)
+cudaError_t launch_tile_pass(int mode, int interp, const PassArgs& a, cudaStream_t stream, int variant)
 {
-    if (!force_generic && a.d_log2 == 0 && a.vec_ok) return launch_tile_pass_fast(mode, interp, a, stream);
+    if (variant != kTileGeneric && a.d_log2 == 0 && a.vec_ok) {
+        if (variant == kTileTma) {
+            bool used = false;
+            const cudaError_t e = launch_tile_pass_tma(mode, interp, a, stream, &used);
+            if (e != cudaSuccess || used) return e;
+        }
+        return launch_tile_pass_fast(mode, interp, a, stream);
+    }
     if (mode == kModeEncode)
         return interp == kInterpLeftTop ? launch_t<kModeEncode, kInterpLeftTop>(a, stream)
                                         : launch_t<kModeEncode, kInterpCrossed>(a, stream);

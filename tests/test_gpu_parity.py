@@ -24,8 +24,9 @@ def ctxs():
     tile = hgi.Context(0, hgi.PATH_TILE)
     lvl = hgi.Context(0, hgi.PATH_PER_LEVEL)
     gen = hgi.Context(0, hgi.PATH_TILE_GENERIC)
-    yield {"tile": tile, "level": lvl, "generic": gen}
-    for c in (tile, lvl, gen):
+    pre = hgi.Context(0, hgi.PATH_TILE_TMA)
+    yield {"tile": tile, "level": lvl, "generic": gen, "tma": pre}
+    for c in (tile, lvl, gen, pre):
         c.close()
 
 
@@ -49,7 +50,7 @@ def check_case(ctx, img, levels, q, interp=oc.INTERP_CROSSED, qkind=oc.QUANT_LIN
     return grid, dec
 
 
-@pytest.mark.parametrize("path", ["tile", "level", "generic"])
+@pytest.mark.parametrize("path", ["tile", "level", "generic", "tma"])
 def test_reference_unit_fixture_all_levels(ctxs, path):
     """src/lib.rs:45-97 `test_error` on the 12x8 (x*y) image at levels=3 -- with the comparison
     against the *source* image that the reference's shadowed variable prevented."""
@@ -62,7 +63,7 @@ def test_reference_unit_fixture_all_levels(ctxs, path):
         assert (grid.as_plane() == oc.encode(img, 3, qlevel=int(q))).all()
 
 
-@pytest.mark.parametrize("path", ["tile", "level", "generic"])
+@pytest.mark.parametrize("path", ["tile", "level", "generic", "tma"])
 def test_golden_cases(ctxs, golden, path):
     for cs in golden["cases"]:
         img = get_plane(cs["plane"])
@@ -76,7 +77,7 @@ SIZES = [(1, 1), (1, 9), (9, 1), (2, 2), (3, 5), (16, 16), (17, 17), (127, 63), 
          (144, 80), (145, 81), (250, 243), (256, 128), (257, 129), (272, 144), (300, 70), (1000, 3), (5, 700)]
 
 
-@pytest.mark.parametrize("path", ["tile", "level", "generic"])
+@pytest.mark.parametrize("path", ["tile", "level", "generic", "tma"])
 @pytest.mark.parametrize("w,h", SIZES)
 def test_ragged_sizes(ctxs, path, w, h):
     img = photo_like(w, h, seed=w * 1000 + h)
@@ -86,7 +87,7 @@ def test_ragged_sizes(ctxs, path, w, h):
     check_case(ctxs[path], img, 6, 0, qkind=oc.QUANT_NOOP)
 
 
-@pytest.mark.parametrize("path", ["tile", "level", "generic"])
+@pytest.mark.parametrize("path", ["tile", "level", "generic", "tma"])
 def test_level_extremes(ctxs, path):
     img = photo_like(200, 120, 4)
     for levels in (0, 8, 12, 20, 30):
@@ -100,7 +101,7 @@ def test_level_extremes(ctxs, path):
         check_case(ctxs[path], sat, 4, q)
 
 
-@pytest.mark.parametrize("path", ["tile", "level", "generic"])
+@pytest.mark.parametrize("path", ["tile", "level", "generic", "tma"])
 def test_aligned_multi_tile_planes(ctxs, path):
     """Widths that take the 128-bit path, several tiles in x and y, two passes (L > 4)."""
     for (w, h, levels, q) in [(512, 256, 4, 2), (640, 200, 6, 3), (1024, 520, 8, 1), (400, 400, 4, 1),
