@@ -102,7 +102,7 @@ static cudaError_t launch_level_t(const LevelArgs& a, cudaStream_t stream)
     if (MODE == kModeDecode || a.quant_error == 0)
         hgi_level_kernel<MODE, INTERP, true><<<grid, block, 0, stream>>>(a);
     else
-        hgi_level_kernel<MODE, INTERP, false><<<grid, block, 0, stream>>>(a);
+        hgi_level_kernel<kModeEncode, INTERP, false><<<grid, block, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

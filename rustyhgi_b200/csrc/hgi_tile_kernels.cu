@@ -225,7 +225,7 @@ cudaError_t launch_t(const PassArgs& a, cudaStream_t stream)
     if (MODE == kModeDecode || a.quant_error == 0)
         hgi_tile_kernel<MODE, INTERP, true><<<(uint32_t)nblocks, NT, 0, stream>>>(a);
     else
-        hgi_tile_kernel<MODE, INTERP, false><<<(uint32_t)nblocks, NT, 0, stream>>>(a);
+        hgi_tile_kernel<kModeEncode, INTERP, false><<<(uint32_t)nblocks, NT, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
