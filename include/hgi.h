@@ -182,6 +182,15 @@ size_t hgi_archive_bound(size_t n);
    (src/grid.rs:4).  On success *out_len = bytes written. */
 int hgi_archive_serialize(const hgi_metadata_t *metadata, const uint8_t *grid, size_t grid_len,
                           uint64_t grid_width, uint8_t *out, size_t out_capacity, size_t *out_len);
+/* The same container with the entropy stage north_star describes: the residual frequency tables come from
+   the GPU (hgi_histogram_* or the `hist_out` of encode) and the host only bit-packs.  `hist` holds `n_blocks`
+   256-bin tables; table b describes grid bytes [b*block_bytes, min(grid_len, (b+1)*block_bytes)) (n_blocks == 1:
+   the whole grid) and each block becomes one dynamic-Huffman DEFLATE block (literals only, no LZ77).  The
+   result is a raw DEFLATE stream any inflate reads, i.e. `Archive::deserialize_from_reader` accepts it. */
+size_t hgi_archive_huffman_bound(size_t n, size_t n_blocks);
+int hgi_archive_serialize_huffman(const hgi_metadata_t *metadata, const uint8_t *grid, size_t grid_len,
+                                  uint64_t grid_width, const uint32_t *hist, size_t n_blocks, size_t block_bytes,
+                                  uint8_t *out, size_t out_capacity, size_t *out_len);
 /* `Archive::deserialize_from_reader` (src/archive.rs:43-55), split so the caller can allocate:
    _header parses MAGIC + metadata (28 bytes); _grid inflates the payload into `grid_out`. */
 int hgi_archive_read_header(const uint8_t *data, size_t len, hgi_metadata_t *metadata_out);

@@ -355,17 +355,37 @@ class Archive:
     def __eq__(self, other):
         return isinstance(other, Archive) and self.metadata == other.metadata and self.grid == other.grid
 
-    def serialize_to_writer(self, w):
+    def serialize_to_writer(self, w, entropy="deflate", hist=None, block_rows=None, ctx=None):
+        """entropy="deflate": zlib level-9 raw DEFLATE (the stand-in for flate2's Compression::best()).
+        entropy="huffman": GPU-built frequency tables + host bit-packing (hgi_archive_serialize_huffman);
+        `hist` may carry the (n_blocks, 256) tables already produced by encode, else they are computed on the
+        GPU here, one table per `block_rows` grid rows (default: one table for the whole grid)."""
         L = _lib.lib()
         buf = self.grid.buffer
-        cap = L.hgi_archive_bound(buf.size)
-        out = np.empty(cap, np.uint8)
         n = ctypes.c_size_t(0)
         m = self.metadata._struct()
-        rc = L.hgi_archive_serialize(ctypes.byref(m), buf.ctypes.data, buf.size, self.grid.width, out.ctypes.data,
-                                     cap, ctypes.byref(n))
-        if rc:
-            raise HgiError(rc, "hgi_archive_serialize")
+        if entropy == "deflate":
+            cap = L.hgi_archive_bound(buf.size)
+            out = np.empty(cap, np.uint8)
+            rc = L.hgi_archive_serialize(ctypes.byref(m), buf.ctypes.data, buf.size, self.grid.width, out.ctypes.data,
+                                         cap, ctypes.byref(n))
+            if rc:
+                raise HgiError(rc, "hgi_archive_serialize")
+        elif entropy == "huffman":
+            block = buf.size if not block_rows else int(block_rows) * self.grid.width
+            block = max(1, min(block, max(buf.size, 1)))
+            n_blocks = max(1, -(-buf.size // block))
+            if hist is None:
+                hist = np.stack([histogram(buf[b * block:(b + 1) * block], ctx=ctx) for b in range(n_blocks)])
+            hist = np.ascontiguousarray(np.asarray(hist).reshape(n_blocks, 256), dtype=np.uint32)
+            cap = L.hgi_archive_huffman_bound(buf.size, n_blocks)
+            out = np.empty(cap, np.uint8)
+            rc = L.hgi_archive_serialize_huffman(ctypes.byref(m), buf.ctypes.data, buf.size, self.grid.width,
+                                                 hist.ctypes.data, n_blocks, block, out.ctypes.data, cap, ctypes.byref(n))
+            if rc:
+                raise HgiError(rc, "hgi_archive_serialize_huffman")
+        else:
+            raise ValueError("entropy must be 'deflate' or 'huffman'")
         w.write(out[:n.value].tobytes())
 
     @classmethod

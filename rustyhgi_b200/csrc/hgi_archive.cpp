@@ -9,6 +9,7 @@
 // stream with flate2's miniz backend is NOT claimed (DESIGN.md "parity unpinned: archive bytes");
 // header bytes and inflate(payload) are exact, and either side can read the other's files.
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 #include <zlib.h>
@@ -23,6 +24,149 @@ uint32_t get_u32(const uint8_t* p) { uint32_t v = 0; for (int i = 0; i < 4; ++i)
 uint64_t get_u64(const uint8_t* p) { uint64_t v = 0; for (int i = 0; i < 8; ++i) v |= (uint64_t)p[i] << (8 * i); return v; }
 
 }  // namespace
+
+// ---- Huffman-only DEFLATE driven by GPU-built frequency tables --------------------------------------------
+// north_star: "archive.rs residue histogram / frequency-table construction [on the GPU] ... the entropy
+// bitstream stays [on the host] after the GPU-built tables".  Each block of residual bytes becomes one
+// dynamic-Huffman DEFLATE block (RFC 1951 3.2.7) whose literal code is built from that block's 256-bin
+// histogram -- no LZ77 matching, so the host only bit-packs.  Any inflate (zlib, flate2/miniz) reads it.
+class BitWriter {
+public:
+    BitWriter(uint8_t* out, size_t cap) : p_(out), end_(out + cap) {}
+    inline void put(uint32_t bits, int n)   // LSB-first, n <= 32
+    {
+        acc_ |= (uint64_t)bits << nbits_;
+        nbits_ += n;
+        while (nbits_ >= 8) {
+            if (p_ < end_) *p_ = (uint8_t)acc_; else overflow_ = true;
+            ++p_;
+            acc_ >>= 8;
+            nbits_ -= 8;
+        }
+    }
+    void finish() { if (nbits_ > 0) put(0, 8 - nbits_); }
+    bool overflow() const { return overflow_; }
+    uint8_t* pos() const { return p_; }
+private:
+    uint8_t *p_, *end_;
+    uint64_t acc_ = 0;
+    int nbits_ = 0;
+    bool overflow_ = false;
+};
+
+// Huffman code lengths (<= max_len) for `n` symbols; zero-frequency symbols get length 0.  Plain heap
+// construction; if the tree is too deep the small counts are flattened and it is rebuilt (rarely needed).
+void huffman_lengths(const uint64_t* freq, int n, int max_len, uint8_t* len_out)
+{
+    std::vector<uint64_t> f(freq, freq + n);
+    for (;;) {
+        std::vector<int> parent(2 * n, -1);
+        std::vector<uint64_t> w(2 * n, 0);
+        std::vector<int> heap;
+        auto less = [&](int a, int b) { return w[a] > w[b] || (w[a] == w[b] && a > b); };
+        for (int i = 0; i < n; ++i)
+            if (f[i]) { w[i] = f[i]; heap.push_back(i); }
+        std::fill(len_out, len_out + n, 0);
+        if (heap.empty()) return;
+        if (heap.size() == 1) { len_out[heap[0]] = 1; return; }
+        std::make_heap(heap.begin(), heap.end(), less);
+        int next = n;
+        while (heap.size() > 1) {
+            std::pop_heap(heap.begin(), heap.end(), less); const int a = heap.back(); heap.pop_back();
+            std::pop_heap(heap.begin(), heap.end(), less); const int b = heap.back(); heap.pop_back();
+            w[next] = w[a] + w[b];
+            parent[a] = parent[b] = next;
+            heap.push_back(next);
+            std::push_heap(heap.begin(), heap.end(), less);
+            ++next;
+        }
+        int deepest = 0;
+        for (int i = 0; i < n; ++i) {
+            if (!f[i]) continue;
+            int d = 0;
+            for (int v = i; parent[v] >= 0; v = parent[v]) ++d;
+            len_out[i] = (uint8_t)d;
+            if (d > deepest) deepest = d;
+        }
+        if (deepest <= max_len) return;
+        for (int i = 0; i < n; ++i)
+            if (f[i]) f[i] = (f[i] >> 2) + 1;   // flatten and retry
+    }
+}
+
+// Canonical codes (RFC 1951 3.2.2), bit-reversed for the LSB-first stream.
+void canonical_codes(const uint8_t* len, int n, uint16_t* code_out)
+{
+    int bl_count[16] = {0};
+    for (int i = 0; i < n; ++i) bl_count[len[i]]++;
+    bl_count[0] = 0;
+    int next_code[16] = {0}, code = 0;
+    for (int b = 1; b <= 15; ++b) { code = (code + bl_count[b - 1]) << 1; next_code[b] = code; }
+    for (int i = 0; i < n; ++i) {
+        if (!len[i]) { code_out[i] = 0; continue; }
+        int c = next_code[len[i]]++, r = 0;
+        for (int b = 0; b < len[i]; ++b) { r = (r << 1) | (c & 1); c >>= 1; }
+        code_out[i] = (uint16_t)r;
+    }
+}
+
+// One dynamic-Huffman block holding `pre` + `data` + `post` as literals, code built from `freq[257]`.
+void write_huffman_block(BitWriter& bw, const uint64_t freq[257], const uint8_t* pre, size_t npre, const uint8_t* data,
+                         size_t n, const uint8_t* post, size_t npost, bool final_block)
+{
+    uint8_t lit_len[257];
+    uint16_t lit_code[257];
+    huffman_lengths(freq, 257, 15, lit_len);
+    canonical_codes(lit_len, 257, lit_code);
+    // lengths to transmit: 257 literal/length codes + 1 distance code (length 1: "one distance code ... using one bit")
+    uint8_t seq[258];
+    std::memcpy(seq, lit_len, 257);
+    seq[257] = 1;
+    // run-length encode with symbols 16/17/18 (3.2.7)
+    struct Tok { uint8_t sym, extra_bits; uint16_t extra; };
+    std::vector<Tok> toks;
+    for (int i = 0; i < 258;) {
+        const uint8_t v = seq[i];
+        int run = 1;
+        while (i + run < 258 && seq[i + run] == v) ++run;
+        int left = run;
+        if (v == 0) {
+            while (left >= 11) { const int r = left > 138 ? 138 : left; toks.push_back({18, 7, (uint16_t)(r - 11)}); left -= r; }
+            if (left >= 3) { toks.push_back({17, 3, (uint16_t)(left - 3)}); left = 0; }
+            while (left-- > 0) toks.push_back({0, 0, 0});
+        } else {
+            toks.push_back({v, 0, 0});
+            --left;
+            while (left >= 3) { const int r = left > 6 ? 6 : left; toks.push_back({16, 2, (uint16_t)(r - 3)}); left -= r; }
+            while (left-- > 0) toks.push_back({v, 0, 0});
+        }
+        i += run;
+    }
+    uint64_t cl_freq[19] = {0};
+    for (const Tok& t : toks) cl_freq[t.sym]++;
+    uint8_t cl_len[19];
+    uint16_t cl_code[19];
+    huffman_lengths(cl_freq, 19, 7, cl_len);
+    canonical_codes(cl_len, 19, cl_code);
+    static const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    int hclen = 19;
+    while (hclen > 4 && cl_len[order[hclen - 1]] == 0) --hclen;
+    bw.put(final_block ? 1u : 0u, 1);   // BFINAL
+    bw.put(2u, 2);                      // BTYPE = 10 (dynamic Huffman)
+    bw.put(257 - 257, 5);               // HLIT
+    bw.put(1 - 1, 5);                   // HDIST
+    bw.put((uint32_t)(hclen - 4), 4);   // HCLEN
+    for (int i = 0; i < hclen; ++i) bw.put(cl_len[order[i]], 3);
+    for (const Tok& t : toks) {
+        bw.put(cl_code[t.sym], cl_len[t.sym]);
+        if (t.extra_bits) bw.put(t.extra, t.extra_bits);
+    }
+    auto emit = [&](const uint8_t* p, size_t m) { for (size_t i = 0; i < m; ++i) bw.put(lit_code[p[i]], lit_len[p[i]]); };
+    emit(pre, npre);
+    emit(data, n);
+    emit(post, npost);
+    bw.put(lit_code[256], lit_len[256]);   // end of block
+}
 
 extern "C" {
 
@@ -80,6 +224,50 @@ int hgi_archive_serialize(const hgi_metadata_t* m, const uint8_t* grid, size_t g
     deflateEnd(&zs);
     if (rc != HGI_OK) return rc;
     *out_len = out_capacity - out_left;
+    return HGI_OK;
+}
+
+size_t hgi_archive_huffman_bound(size_t n, size_t n_blocks)
+{
+    // <= 15 bits per literal, <= ~330 bytes of table per block, 16 bincode bytes, header
+    return HGI_ARCHIVE_HEADER_BYTES + 2 * (n + 16) + 512 * (n_blocks ? n_blocks : 1) + 64;
+}
+
+int hgi_archive_serialize_huffman(const hgi_metadata_t* m, const uint8_t* grid, size_t grid_len, uint64_t grid_width,
+                                  const uint32_t* hist, size_t n_blocks, size_t block_bytes, uint8_t* out,
+                                  size_t out_capacity, size_t* out_len)
+{
+    if (!m || !out || !out_len || !hist || n_blocks == 0 || (grid_len && !grid)) return HGI_ERR_INVALID_ARG;
+    if (m->quantization_level > 3 || m->interpolation > 2) return HGI_ERR_INVALID_ARG;
+    if (n_blocks > 1 && (block_bytes == 0 || (n_blocks - 1) * block_bytes >= grid_len || n_blocks * block_bytes < grid_len))
+        return HGI_ERR_INVALID_ARG;
+    if (out_capacity < HGI_ARCHIVE_HEADER_BYTES) return HGI_ERR_BUFFER_TOO_SMALL;
+    put_u32(out + 0, HGI_ARCHIVE_MAGIC);
+    put_u32(out + 4, m->quantization_level);
+    put_u32(out + 8, m->interpolation);
+    put_u32(out + 12, m->width);
+    put_u32(out + 16, m->height);
+    put_u64(out + 20, m->scale_level);
+    uint8_t lenb[8], widthb[8];
+    put_u64(lenb, (uint64_t)grid_len);       // bincode(Grid): Vec<u8> length prefix, bytes, then `width: usize`
+    put_u64(widthb, grid_width);
+    BitWriter bw(out + HGI_ARCHIVE_HEADER_BYTES, out_capacity - HGI_ARCHIVE_HEADER_BYTES);
+    for (size_t b = 0; b < n_blocks; ++b) {
+        const size_t lo = n_blocks == 1 ? 0 : b * block_bytes;
+        const size_t hi = (n_blocks == 1 || b + 1 == n_blocks) ? grid_len : lo + block_bytes;
+        uint64_t freq[257];
+        uint64_t total = 0;
+        for (int i = 0; i < 256; ++i) { freq[i] = hist[b * 256 + i]; total += freq[i]; }
+        if (total != hi - lo) return HGI_ERR_INVALID_ARG;   // the table must describe exactly this block
+        freq[256] = 1;                                       // end-of-block
+        const bool first = (b == 0), last = (b + 1 == n_blocks);
+        if (first) for (int i = 0; i < 8; ++i) freq[lenb[i]]++;
+        if (last) for (int i = 0; i < 8; ++i) freq[widthb[i]]++;
+        write_huffman_block(bw, freq, lenb, first ? 8 : 0, grid + lo, hi - lo, widthb, last ? 8 : 0, last);
+    }
+    bw.finish();
+    if (bw.overflow()) return HGI_ERR_BUFFER_TOO_SMALL;
+    *out_len = (size_t)(bw.pos() - out);
     return HGI_OK;
 }
 

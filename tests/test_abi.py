@@ -95,6 +95,46 @@ def test_archive_large_and_foreign_stream():
     assert hgi.Archive.deserialize_from_reader(io.BytesIO(foreign)).grid == hgi.Grid(grid, 600)
 
 
+@pytest.mark.parametrize("block_rows", [None, 7, 64])
+def test_archive_huffman_entropy_stage(block_rows):
+    """Frequency tables in, bit-packed dynamic-Huffman DEFLATE out (hgi_archive_serialize_huffman).  Here the
+    tables are counted with numpy; tests/test_gpu_next_rows.py feeds the GPU-built ones."""
+    rng = np.random.default_rng(4)
+    for h, w, levels, q in ((64, 48, 3, 2), (300, 200, 4, 3), (1, 1, 0, 0), (97, 13, 4, 0)):
+        grid = oc.encode(rng.integers(0, 256, (h, w)).astype(np.uint8) // (1 if q == 0 else 6), levels, qlevel=q)
+        buf = grid.reshape(-1)
+        block = buf.size if not block_rows else block_rows * w
+        nb = max(1, -(-buf.size // block))
+        hist = np.stack([np.bincount(buf[b * block:(b + 1) * block], minlength=256) for b in range(nb)])
+        md = hgi.Metadata(q, 0, w, h, levels)
+        out = io.BytesIO()
+        hgi.Archive(md, hgi.Grid(grid, w)).serialize_to_writer(out, entropy="huffman", hist=hist, block_rows=block_rows)
+        raw = out.getvalue()
+        assert raw[:4].hex() == "55a5adba"
+        payload = zlib.decompress(raw[28:], -15)                  # a conforming inflate (flate2/miniz, zlib) reads it
+        assert payload == buf.size.to_bytes(8, "little") + buf.tobytes() + w.to_bytes(8, "little")
+        assert hgi.Archive.deserialize_from_reader(io.BytesIO(raw)) == hgi.Archive(md, hgi.Grid(grid, w))
+    # a table that does not describe the block is rejected
+    bad = hist.copy()
+    bad[0, 0] += 1
+    with pytest.raises(hgi.HgiError):
+        hgi.Archive(md, hgi.Grid(grid, w)).serialize_to_writer(io.BytesIO(), entropy="huffman", hist=bad,
+                                                                block_rows=block_rows)
+
+
+def test_archive_huffman_skewed_tables_respect_length_limit():
+    """Fibonacci-like counts would give code lengths > 15 without the length limit."""
+    counts = [1, 1]
+    while len(counts) < 40:
+        counts.append(counts[-1] + counts[-2])
+    data = np.concatenate([np.full(c, i, np.uint8) for i, c in enumerate(counts[:30])])
+    hist = np.bincount(data, minlength=256)[None, :]
+    out = io.BytesIO()
+    hgi.Archive(hgi.Metadata(0, 0, data.size, 1, 0), hgi.Grid(data, data.size)).serialize_to_writer(
+        out, entropy="huffman", hist=hist)
+    assert zlib.decompress(out.getvalue()[28:], -15)[8:-8] == data.tobytes()
+
+
 def test_archive_errors():
     with pytest.raises(hgi.HgiError) as e:
         hgi.Archive.deserialize_from_reader(io.BytesIO(b"\x00\x01\x02\x03" + bytes(40)))

@@ -40,6 +40,25 @@ def test_docs_source_image_luma_matches_golden():
     assert (hgi.rgb_to_luma(rgb) == oc.rgb_to_luma(rgb)).all()
 
 
+def test_archive_with_gpu_built_frequency_tables():
+    """f-1: encode on the GPU with fused per-image histograms, entropy-code on the host from those tables."""
+    img = load_plane("fullhd")
+    enc = hgi.Encoder(hgi.Crossed, hgi.Linear(hgi.QuantizationLevel.Medium), 4)
+    grids, hist = enc.encode_batch(img[None], want_hist=True)
+    md = hgi.Metadata(2, 0, 1920, 1080, 4)
+    arch = hgi.Archive(md, hgi.Grid(grids[0], 1920))
+    out = io.BytesIO()
+    arch.serialize_to_writer(out, entropy="huffman", hist=hist)          # one table for the whole grid
+    assert hgi.Archive.deserialize_from_reader(io.BytesIO(out.getvalue())) == arch
+    out2 = io.BytesIO()
+    arch.serialize_to_writer(out2, entropy="huffman", block_rows=120)    # nine tables, built by hgi_histogram_u8
+    raw = out2.getvalue()
+    assert zlib.decompress(raw[28:], -15)[8:-8] == grids[0].tobytes()
+    assert len(raw) < img.size // 4                                       # sanity: it does compress
+    after = hgi.Decoder(hgi.Crossed).decode((1920, 1080), 4, hgi.Archive.deserialize_from_reader(io.BytesIO(raw)).grid)
+    assert sha16(after) == "96db2c544587bccb"
+
+
 def test_cli_test_subcommand_config1(tmp_path, monkeypatch, capsys):
     """BASELINE config 1: `hgi test res/LENA.TIF` (level 4, Medium) -> `Uncompressed: 64 kb`, `SD: 9.17`."""
     monkeypatch.chdir(tmp_path)
