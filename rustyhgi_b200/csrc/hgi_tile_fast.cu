@@ -40,7 +40,62 @@ namespace {
 #define HGI_FAST_MIN_BLOCKS 10
 #endif
 
-template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV>
+// 16-pixel chunk I/O.  ALIGNED (w % 16 == 0, 16-byte-aligned bases): one 128-bit access, `nvalid` is 0 or 16.
+// Otherwise (any width / alignment): complete chunks use 32-bit accesses -- directly when the address is
+// 4-byte aligned, else five aligned loads funnel-shifted into place (`may_overread` says the 1..3 bytes after the
+// chunk are still inside the plane batch) / aligned middle words plus byte head and tail for stores; ragged chunks
+// at the right image edge use byte accesses.  Bytes beyond the image read as 0 and are never written.
+template <bool ALIGNED>
+__device__ __forceinline__ uint4 load_chunk(const uint8_t* __restrict__ ptr, int nvalid, bool may_overread)
+{
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (nvalid <= 0) return v;
+    if (ALIGNED) return __ldg(reinterpret_cast<const uint4*>(ptr));
+    const uint32_t sh = (uint32_t)((uintptr_t)ptr & 3u);
+    if (nvalid >= 16 && (sh == 0 || may_overread)) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(ptr - sh);
+        const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3);
+        if (sh == 0) return make_uint4(w0, w1, w2, w3);
+        const uint32_t w4 = __ldg(q + 4), s8 = 8 * sh;
+        return make_uint4(__funnelshift_r(w0, w1, s8), __funnelshift_r(w1, w2, s8), __funnelshift_r(w2, w3, s8),
+                          __funnelshift_r(w3, w4, s8));
+    }
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if (i < nvalid) w[i >> 2] |= (uint32_t)__ldg(ptr + i) << (8 * (i & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <bool ALIGNED>
+__device__ __forceinline__ void store_chunk(uint8_t* __restrict__ ptr, const uint32_t (&w)[4], int nvalid)
+{
+    if (nvalid <= 0) return;
+    if (ALIGNED) {
+        *reinterpret_cast<uint4*>(ptr) = make_uint4(w[0], w[1], w[2], w[3]);
+        return;
+    }
+    const uint32_t sh = (uint32_t)((uintptr_t)ptr & 3u);
+    if (nvalid >= 16 && sh == 0) {
+        uint32_t* q = reinterpret_cast<uint32_t*>(ptr);
+        q[0] = w[0]; q[1] = w[1]; q[2] = w[2]; q[3] = w[3];
+    } else if (nvalid >= 16) {
+        // head: 4 - sh bytes up to the next aligned address, three aligned words, tail: sh bytes
+        const uint32_t hb = 4u - sh, s8 = 8 * hb;
+        for (uint32_t i = 0; i < hb; ++i) ptr[i] = (uint8_t)(w[0] >> (8 * i));
+        uint32_t* q = reinterpret_cast<uint32_t*>(ptr + hb);
+        q[0] = __funnelshift_r(w[0], w[1], s8);
+        q[1] = __funnelshift_r(w[1], w[2], s8);
+        q[2] = __funnelshift_r(w[2], w[3], s8);
+        for (uint32_t i = 0; i < sh; ++i) ptr[12 + hb + i] = (uint8_t)(w[3] >> (8 * (hb + i)));
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < nvalid) ptr[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+    }
+}
+
+template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED>
 __global__ void __launch_bounds__(NT, HGI_FAST_MIN_BLOCKS)
 hgi_tile_fast_kernel(const PassArgs p)
 {
@@ -61,16 +116,17 @@ hgi_tile_fast_kernel(const PassArgs p)
 
     // ---- 1. global loads: this thread's NU 16x2-pixel units (kept in registers for the finest level) ----
     const int sx = tid & 7, ry = tid >> 3;          // 8 column strips x RPB row pairs (x NU unit blocks)
-    const bool col_ok = 16 * sx < xin;
+    const int nvalid = max(0, min(16, xin - 16 * sx));   // in-image bytes of this thread's chunks (0 or 16 if ALIGNED)
     const uint32_t toff = (uint32_t)(2 * ry) * p.w + (uint32_t)(16 * sx);   // tile-relative, fits 32 bits
     uint4 ev[NU], od[NU];
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
-        ev[u] = make_uint4(0u, 0u, 0u, 0u);
-        od[u] = make_uint4(0u, 0u, 0u, 0u);
         const int y = 2 * ry + 2 * RPB * u;
-        if (col_ok && y < yin) ev[u] = __ldg(reinterpret_cast<const uint4*>(tile + toff + (uint32_t)(2 * RPB * u) * p.w));
-        if (col_ok && y + 1 < yin) od[u] = __ldg(reinterpret_cast<const uint4*>(tile + toff + (uint32_t)(2 * RPB * u + 1) * p.w));
+        // a complete chunk may be over-read by <= 3 bytes unless it ends the very last row of the batch
+        const bool last0 = (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 1 >= p.h) && (X0 + 16u * sx + 16u >= p.w);
+        const bool last1 = (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 2 >= p.h) && (X0 + 16u * sx + 16u >= p.w);
+        ev[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * RPB * u) * p.w, y < yin ? nvalid : 0, !last0);
+        od[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * RPB * u + 1) * p.w, y + 1 < yin ? nvalid : 0, !last1);
     }
 
     // halo chunks (right of / below the tile) feed only the coarse planes; the upper half of the CTA
@@ -85,8 +141,8 @@ hgi_tile_fast_kernel(const PassArgs p)
     }
     const bool halo = NLEV > 1 && hj >= 0 && hj < NHALO;
     uint4 hv = make_uint4(0u, 0u, 0u, 0u);
-    if (halo && hy < yin && 16 * hc < xin)
-        hv = __ldg(reinterpret_cast<const uint4*>(tile + (uint32_t)hy * p.w + (uint32_t)(16 * hc)));
+    if (halo && hy < yin)
+        hv = load_chunk<ALIGNED>(tile + (uint32_t)hy * p.w + (uint32_t)(16 * hc), min(16, xin - 16 * hc), false);
 
     // ---- 2. stage the dense coarse planes + the coarse lattice of this pass ---------------------
 #pragma unroll
@@ -170,21 +226,22 @@ hgi_tile_fast_kernel(const PassArgs p)
                 out_od[k] = interleave(decode2(a2, pr), decode2(a3, pr));
             }
         }
-        if (col_ok && row0_ok) *reinterpret_cast<uint4*>(out + uoff) = make_uint4(out_ev[0], out_ev[1], out_ev[2], out_ev[3]);
-        if (col_ok && row1_ok) *reinterpret_cast<uint4*>(out + uoff + p.w) = make_uint4(out_od[0], out_od[1], out_od[2], out_od[3]);
+        store_chunk<ALIGNED>(out + uoff, out_ev, row0_ok ? nvalid : 0);
+        store_chunk<ALIGNED>(out + uoff + p.w, out_od, row1_ok ? nvalid : 0);
         if (MODE == kModeEncode && EXTRA) {
             if (p.recon_out != nullptr) {
                 uint8_t* __restrict__ rout = p.recon_out + tile_off;
-                if (col_ok && row0_ok) *reinterpret_cast<uint4*>(rout + uoff) = make_uint4(rec_ev[0], rec_ev[1], rec_ev[2], rec_ev[3]);
-                if (col_ok && row1_ok) *reinterpret_cast<uint4*>(rout + uoff + p.w) = make_uint4(rec_od[0], rec_od[1], rec_od[2], rec_od[3]);
+                store_chunk<ALIGNED>(rout + uoff, rec_ev, row0_ok ? nvalid : 0);
+                store_chunk<ALIGNED>(rout + uoff + p.w, rec_od, row1_ok ? nvalid : 0);
             }
             // residual histogram (north_star's archive.rs stage): warp-private shared-memory bins
-            if (p.hist != nullptr && col_ok) {
+            if (p.hist != nullptr && nvalid > 0) {
                 uint32_t* mine = &whist[(tid >> 5) * 256];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
+                        if (4 * k + b >= nvalid) continue;
                         if (row0_ok) atomicAdd(&mine[(out_ev[k] >> (8 * b)) & 0xFFu], 1u);
                         if (row1_ok) atomicAdd(&mine[(out_od[k] >> (8 * b)) & 0xFFu], 1u);
                     }
@@ -203,7 +260,7 @@ hgi_tile_fast_kernel(const PassArgs p)
     }
 }
 
-template <int MODE, int INTERP, int NLEV>
+template <int MODE, int INTERP, int NLEV, bool ALIGNED>
 cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
 {
     const uint32_t tiles_x = (args.w + TW - 1) / TW, tiles_y = (args.h + TH - 1) / TH;
@@ -221,14 +278,14 @@ cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
         if (args.c_q) a.c_q = args.c_q + (size_t)first * args.cw * args.ch;
         const dim3 nb(tiles_x, tiles_y, a.n_images);
         if (MODE == kModeDecode) {
-            hgi_tile_fast_kernel<kModeDecode, INTERP, true, false, NLEV><<<nb, NT, 0, stream>>>(a);
+            hgi_tile_fast_kernel<kModeDecode, INTERP, true, false, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a);
         } else {
             const bool extra = (a.recon_out != nullptr) || (a.hist != nullptr);
             const bool ident = (a.quant_error == 0);
-            if (ident && !extra) hgi_tile_fast_kernel<kModeEncode, INTERP, true, false, NLEV><<<nb, NT, 0, stream>>>(a);
-            else if (ident) hgi_tile_fast_kernel<kModeEncode, INTERP, true, true, NLEV><<<nb, NT, 0, stream>>>(a);
-            else if (!extra) hgi_tile_fast_kernel<kModeEncode, INTERP, false, false, NLEV><<<nb, NT, 0, stream>>>(a);
-            else hgi_tile_fast_kernel<kModeEncode, INTERP, false, true, NLEV><<<nb, NT, 0, stream>>>(a);
+            if (ident && !extra) hgi_tile_fast_kernel<kModeEncode, INTERP, true, false, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a);
+            else if (ident) hgi_tile_fast_kernel<kModeEncode, INTERP, true, true, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a);
+            else if (!extra) hgi_tile_fast_kernel<kModeEncode, INTERP, false, false, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a);
+            else hgi_tile_fast_kernel<kModeEncode, INTERP, false, true, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a);
         }
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -239,11 +296,20 @@ cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
 template <int MODE, int INTERP>
 cudaError_t launch_fast_t(const PassArgs& a, cudaStream_t stream)
 {
-    switch (a.nlev) {
-        case 1: return launch_fast_n<MODE, INTERP, 1>(a, stream);
-        case 2: return launch_fast_n<MODE, INTERP, 2>(a, stream);
-        case 3: return launch_fast_n<MODE, INTERP, 3>(a, stream);
-        case 4: return launch_fast_n<MODE, INTERP, 4>(a, stream);
+    if (a.vec_ok) {
+        switch (a.nlev) {
+            case 1: return launch_fast_n<MODE, INTERP, 1, true>(a, stream);
+            case 2: return launch_fast_n<MODE, INTERP, 2, true>(a, stream);
+            case 3: return launch_fast_n<MODE, INTERP, 3, true>(a, stream);
+            case 4: return launch_fast_n<MODE, INTERP, 4, true>(a, stream);
+            default: return cudaErrorInvalidValue;
+        }
+    }
+    switch (a.nlev) {   // any width / alignment
+        case 1: return launch_fast_n<MODE, INTERP, 1, false>(a, stream);
+        case 2: return launch_fast_n<MODE, INTERP, 2, false>(a, stream);
+        case 3: return launch_fast_n<MODE, INTERP, 3, false>(a, stream);
+        case 4: return launch_fast_n<MODE, INTERP, 4, false>(a, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -163,6 +163,32 @@ def test_device_api_with_torch(ctxs):
         assert (t.cpu().numpy() == imgs).all()              # input is const (reference consumes a copy)
 
 
+def test_device_api_misaligned_bases_and_odd_widths(ctxs):
+    """Planes whose base address and rows are not 16- (or even 4-) byte aligned take the funnel-shift / byte
+    paths of the SWAR kernel; input, grid and image live at odd offsets inside larger allocations whose guard
+    bytes must stay untouched."""
+    import torch
+    ctx = ctxs["tile"]
+    for (n, h, w, levels, q) in [(2, 70, 160, 4, 2), (3, 65, 131, 3, 1), (1, 129, 255, 5, 3), (2, 64, 128, 4, 0)]:
+        imgs = np.stack([photo_like(w, h, 7 * k + w) for k in range(n)])
+        want_g = oc.encode_batch(imgs, levels, qlevel=q)
+        want_r = oc.decode_batch(want_g, levels)
+        for off in (1, 2, 3, 5):
+            size = n * h * w
+            src = torch.full((size + 64,), 0xAB, dtype=torch.uint8, device="cuda")
+            dst = torch.full((size + 64,), 0xCD, dtype=torch.uint8, device="cuda")
+            out = torch.full((size + 64,), 0xEF, dtype=torch.uint8, device="cuda")
+            src[off:off + size] = torch.from_numpy(imgs).cuda().reshape(-1)
+            s_v, d_v, o_v = (t[off:off + size].view(n, h, w) for t in (src, dst, out))
+            enc = hgi.Encoder(hgi.Crossed, hgi.Linear(Q(q)), levels, ctx=ctx)
+            enc.encode_device(s_v, grids_out=d_v)
+            hgi.Decoder(hgi.Crossed, ctx=ctx).decode_device(levels, d_v, images_out=o_v)
+            torch.cuda.synchronize()
+            assert (d_v.cpu().numpy() == want_g).all() and (o_v.cpu().numpy() == want_r).all()
+            for t, fill in ((dst, 0xCD), (out, 0xEF)):          # nothing written outside the planes
+                assert bool((t[:off] == fill).all()) and bool((t[off + size:] == fill).all())
+
+
 def test_archive_roundtrip_from_gpu_grid(ctxs):
     """`hgi test`-style flow (src/main.rs:73-120) on LENA.TIF level 4 Medium = BASELINE config 1."""
     img = get_plane("lena_tif")
