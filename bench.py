@@ -168,10 +168,36 @@ def cpu_baseline(budget_s=12.0):
             "single_thread_value": W * H / st / 1e6}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank (and first-touch its pinned buffers) on the NUMA node its GPU hangs off, so that 8 ranks
+    streaming over PCIe do not all pull through one socket.  Best effort; returns a note for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id       # e.g. 0000:1B:00.0
+        if isinstance(bus, int):
+            return None
+        base = f"/sys/bus/pci/devices/{bus.lower()}"
+        node = int(open(base + "/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import rustyhgi_b200 as hgi
 
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -302,7 +328,7 @@ def run_ours(args, rank, world, local_rank):
             e2e = {"value": world * len(QLEVELS) * f_e * W * H / dt / 1e6, "unit": UNIT,
                    "h2d_bytes_per_step": bytes_dir, "d2h_bytes_per_step": bytes_dir, "frames_per_gpu": f_e,
                    "pinned_buffer_frames": n_e,
-                   "steps": e_steps, "ms_per_step": dt * 1e3,
+                   "steps": e_steps, "ms_per_step": dt * 1e3, "numa_binding": numa,
                    "api": "hgi_encode_batch_u8 + hgi_decode_batch_u8 (host pointers, pinned)"}
 
     if rank == 0:

@@ -14,7 +14,16 @@
 namespace {
 
 constexpr int kSlots = 3;  // host-API pipeline depth (H2D / kernels / D2H overlap)
-constexpr size_t kChunkBytes = 64u << 20;
+// Bytes per pipeline chunk of the host-pointer entry points; HGI_B200_CHUNK_MB overrides (tuning hook).
+size_t chunk_bytes()
+{
+    static const size_t v = [] {
+        const char* e = std::getenv("HGI_B200_CHUNK_MB");
+        const long mb = e ? std::atol(e) : 0;
+        return (size_t)(mb > 0 && mb <= 4096 ? mb : 64) << 20;
+    }();
+    return v;
+}
 
 struct DevBuf {
     uint8_t* p = nullptr;
@@ -299,7 +308,7 @@ int run_host(hgi_ctx* ctx, int mode, const uint8_t* in, uint32_t n_images, uint3
 {
     const size_t plane = (size_t)w * h;
     if (n_images == 0 || plane == 0) return HGI_OK;
-    uint32_t per = (uint32_t)(kChunkBytes / plane);
+    uint32_t per = (uint32_t)(chunk_bytes() / plane);
     if (per < 1) per = 1;
     if (per > n_images) per = n_images;
     const uint32_t n_chunks = (n_images + per - 1) / per;
