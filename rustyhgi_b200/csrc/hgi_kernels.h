@@ -32,6 +32,10 @@ struct PassArgs {
     uint32_t n_images;
     uint32_t quant_error;    // 0 => identity quantizer
     uint32_t vec_ok;         // D==1 and rows are 16-byte aligned => 128-bit global accesses
+    // source addressing of the SWAR kernel's lattice view (filled by launch_tile_pass_fast): byte distance between
+    // horizontally / vertically adjacent lattice points and between images in `src`
+    uint32_t src_xstride;
+    uint64_t src_pitch, src_plane;
 };
 
 // Dispatch of one pass.  kTileAuto: D == 1 passes on 16-byte-aligned planes go to the register-prefetch SWAR

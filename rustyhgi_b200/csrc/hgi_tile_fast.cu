@@ -67,6 +67,16 @@ __device__ __forceinline__ uint4 load_chunk(const uint8_t* __restrict__ ptr, int
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// Strided gather of one chunk for the D > 1 passes (lattice points are `xs` bytes apart in the plane).
+__device__ __forceinline__ uint4 load_chunk_strided(const uint8_t* __restrict__ ptr, int nvalid, uint32_t xs)
+{
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if (i < nvalid) w[i >> 2] |= (uint32_t)__ldg(ptr + (size_t)i * xs) << (8 * (i & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 template <bool ALIGNED>
 __device__ __forceinline__ void store_chunk(uint8_t* __restrict__ ptr, const uint32_t (&w)[4], int nvalid)
 {
@@ -95,7 +105,9 @@ __device__ __forceinline__ void store_chunk(uint8_t* __restrict__ ptr, const uin
     }
 }
 
-template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED>
+// STRIDED: a D > 1 pass -- p.w / p.h are the lattice dimensions, pixels are gathered with the src_* strides and the
+// results go to the compact planes (grid_out = symbols, recon_out = reconstruction, both with pitch p.w).
+template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED, bool STRIDED>
 __global__ void __launch_bounds__(NT, HGI_FAST_MIN_BLOCKS)
 hgi_tile_fast_kernel(const PassArgs p)
 {
@@ -109,8 +121,11 @@ hgi_tile_fast_kernel(const PassArgs p)
     const int xin = (int)min((uint32_t)(TW + FMAX + 1), p.w - X0);   // in-image extent of tile + halo
     const int yin = (int)min((uint32_t)(TH + FMAX + 1), p.h - Y0);
     const bool edge = (xin < TW + FMAX + 1) || (yin < TH + FMAX + 1);
-    const size_t tile_off = ((size_t)img * p.h + Y0) * p.w + X0;     // CTA-uniform
-    const uint8_t* __restrict__ tile = p.src + tile_off;
+    const size_t tile_off = ((size_t)img * p.h + Y0) * p.w + X0;     // CTA-uniform; offset in the output planes
+    const uint32_t xs = STRIDED ? p.src_xstride : 1u;                // source strides (bytes)
+    const size_t pitch = STRIDED ? (size_t)p.src_pitch : (size_t)p.w;
+    const uint8_t* __restrict__ tile = STRIDED ? p.src + (size_t)img * p.src_plane + (size_t)Y0 * pitch + (size_t)X0 * xs
+                                               : p.src + tile_off;
     const bool top = (p.c_recon == nullptr);
     const QuantSwar qc = quant_swar(p.quant_error);
 
@@ -125,8 +140,14 @@ hgi_tile_fast_kernel(const PassArgs p)
         // a complete chunk may be over-read by <= 3 bytes unless it ends the very last row of the batch
         const bool last0 = (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 1 >= p.h) && (X0 + 16u * sx + 16u >= p.w);
         const bool last1 = (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 2 >= p.h) && (X0 + 16u * sx + 16u >= p.w);
-        ev[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * RPB * u) * p.w, y < yin ? nvalid : 0, !last0);
-        od[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * RPB * u + 1) * p.w, y + 1 < yin ? nvalid : 0, !last1);
+        if (STRIDED) {
+            const uint8_t* r0 = tile + (size_t)y * pitch + (size_t)(16 * sx) * xs;
+            ev[u] = load_chunk_strided(r0, y < yin ? nvalid : 0, xs);
+            od[u] = load_chunk_strided(r0 + pitch, y + 1 < yin ? nvalid : 0, xs);
+        } else {
+            ev[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * RPB * u) * p.w, y < yin ? nvalid : 0, !last0);
+            od[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * RPB * u + 1) * p.w, y + 1 < yin ? nvalid : 0, !last1);
+        }
     }
 
     // halo chunks (right of / below the tile) feed only the coarse planes; the upper half of the CTA
@@ -141,8 +162,12 @@ hgi_tile_fast_kernel(const PassArgs p)
     }
     const bool halo = NLEV > 1 && hj >= 0 && hj < NHALO;
     uint4 hv = make_uint4(0u, 0u, 0u, 0u);
-    if (halo && hy < yin)
-        hv = load_chunk<ALIGNED>(tile + (uint32_t)hy * p.w + (uint32_t)(16 * hc), min(16, xin - 16 * hc), false);
+    if (halo && hy < yin) {
+        if (STRIDED)
+            hv = load_chunk_strided(tile + (size_t)hy * pitch + (size_t)(16 * hc) * xs, min(16, xin - 16 * hc), xs);
+        else
+            hv = load_chunk<ALIGNED>(tile + (uint32_t)hy * p.w + (uint32_t)(16 * hc), min(16, xin - 16 * hc), false);
+    }
 
     // ---- 2. stage the dense coarse planes + the coarse lattice of this pass ---------------------
 #pragma unroll
@@ -159,7 +184,7 @@ hgi_tile_fast_kernel(const PassArgs p)
             uint8_t rv = 0, qv = 0;
             if (x < xin && y < yin) {
                 if (top) {   // src/encoder.rs:26-37 / src/decoder.rs:22-28: the seed is the source byte
-                    rv = __ldg(tile + (uint32_t)y * p.w + (uint32_t)x);
+                    rv = __ldg(tile + (size_t)y * pitch + (size_t)x * xs);
                     qv = rv;
                 } else {
                     const size_t co = (size_t)img * p.cw * p.ch + (size_t)((Y0 + y) >> NLEV) * p.cw + ((X0 + x) >> NLEV);
@@ -260,7 +285,7 @@ hgi_tile_fast_kernel(const PassArgs p)
     }
 }
 
-template <int MODE, int INTERP, int NLEV, bool ALIGNED>
+template <int MODE, int INTERP, int NLEV, bool ALIGNED, bool STRIDED>
 cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
 {
     const uint32_t tiles_x = (args.w + TW - 1) / TW, tiles_y = (args.h + TH - 1) / TH;
@@ -270,7 +295,7 @@ cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
     for (uint32_t first = 0; first < args.n_images; first += 65535u) {   // gridDim.z limit
         PassArgs a = args;
         a.n_images = args.n_images - first < 65535u ? args.n_images - first : 65535u;
-        a.src = args.src + (size_t)first * plane;
+        a.src = args.src + (size_t)first * (STRIDED ? (size_t)args.src_plane : plane);
         if (args.grid_out) a.grid_out = args.grid_out + (size_t)first * plane;
         if (args.recon_out) a.recon_out = args.recon_out + (size_t)first * plane;
         if (args.hist) a.hist = args.hist + (size_t)first * 256;
@@ -278,14 +303,14 @@ cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
         if (args.c_q) a.c_q = args.c_q + (size_t)first * args.cw * args.ch;
         const dim3 nb(tiles_x, tiles_y, a.n_images);
         if (MODE == kModeDecode) {
-            hgi_tile_fast_kernel<kModeDecode, INTERP, true, false, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a);
+            hgi_tile_fast_kernel<kModeDecode, INTERP, true, false, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a);
         } else {
             const bool extra = (a.recon_out != nullptr) || (a.hist != nullptr);
             const bool ident = (a.quant_error == 0);
-            if (ident && !extra) hgi_tile_fast_kernel<kModeEncode, INTERP, true, false, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a);
-            else if (ident) hgi_tile_fast_kernel<kModeEncode, INTERP, true, true, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a);
-            else if (!extra) hgi_tile_fast_kernel<kModeEncode, INTERP, false, false, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a);
-            else hgi_tile_fast_kernel<kModeEncode, INTERP, false, true, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a);
+            if (ident && !extra) hgi_tile_fast_kernel<kModeEncode, INTERP, true, false, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a);
+            else if (ident) hgi_tile_fast_kernel<kModeEncode, INTERP, true, true, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a);
+            else if (!extra) hgi_tile_fast_kernel<kModeEncode, INTERP, false, false, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a);
+            else hgi_tile_fast_kernel<kModeEncode, INTERP, false, true, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a);
         }
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -296,20 +321,39 @@ cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
 template <int MODE, int INTERP>
 cudaError_t launch_fast_t(const PassArgs& a, cudaStream_t stream)
 {
+    if (a.d_log2 > 0) {   // coarse pass: lattice view of the planes, compact outputs
+        PassArgs v = a;
+        v.w = a.wD;
+        v.h = a.hD;
+        v.src_xstride = 1u << a.d_log2;
+        v.src_pitch = (uint64_t)a.w << a.d_log2;
+        v.src_plane = (uint64_t)a.w * a.h;
+        v.grid_out = a.s_q;
+        v.recon_out = a.s_recon;
+        v.hist = nullptr;
+        v.vec_ok = 0;
+        switch (a.nlev) {
+            case 1: return launch_fast_n<MODE, INTERP, 1, false, true>(v, stream);
+            case 2: return launch_fast_n<MODE, INTERP, 2, false, true>(v, stream);
+            case 3: return launch_fast_n<MODE, INTERP, 3, false, true>(v, stream);
+            case 4: return launch_fast_n<MODE, INTERP, 4, false, true>(v, stream);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     if (a.vec_ok) {
         switch (a.nlev) {
-            case 1: return launch_fast_n<MODE, INTERP, 1, true>(a, stream);
-            case 2: return launch_fast_n<MODE, INTERP, 2, true>(a, stream);
-            case 3: return launch_fast_n<MODE, INTERP, 3, true>(a, stream);
-            case 4: return launch_fast_n<MODE, INTERP, 4, true>(a, stream);
+            case 1: return launch_fast_n<MODE, INTERP, 1, true, false>(a, stream);
+            case 2: return launch_fast_n<MODE, INTERP, 2, true, false>(a, stream);
+            case 3: return launch_fast_n<MODE, INTERP, 3, true, false>(a, stream);
+            case 4: return launch_fast_n<MODE, INTERP, 4, true, false>(a, stream);
             default: return cudaErrorInvalidValue;
         }
     }
     switch (a.nlev) {   // any width / alignment
-        case 1: return launch_fast_n<MODE, INTERP, 1, false>(a, stream);
-        case 2: return launch_fast_n<MODE, INTERP, 2, false>(a, stream);
-        case 3: return launch_fast_n<MODE, INTERP, 3, false>(a, stream);
-        case 4: return launch_fast_n<MODE, INTERP, 4, false>(a, stream);
+        case 1: return launch_fast_n<MODE, INTERP, 1, false, false>(a, stream);
+        case 2: return launch_fast_n<MODE, INTERP, 2, false, false>(a, stream);
+        case 3: return launch_fast_n<MODE, INTERP, 3, false, false>(a, stream);
+        case 4: return launch_fast_n<MODE, INTERP, 4, false, false>(a, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -233,10 +233,10 @@ cudaError_t launch_t(const PassArgs& a, cudaStream_t stream)
 
 cudaError_t launch_tile_pass(int mode, int interp, const PassArgs& a, cudaStream_t stream, int variant)
 {
-    // D == 1 passes: SWAR kernels (the prefetch kernel takes any width/alignment, the TMA kernel needs 16-byte rows);
-    // planes taller than 65535 tiles and the strided D > 1 passes stay on the generic kernel
-    if (variant != kTileGeneric && a.d_log2 == 0 && (a.h + 63) / 64 <= 65535u) {
-        if (variant == kTileTma && a.vec_ok) {
+    // SWAR kernels: the prefetch kernel takes any width / alignment and, as a strided lattice view, the D > 1 passes;
+    // the TMA kernel needs D == 1 and 16-byte rows.  Only planes taller than 65535 tiles stay on the generic kernel
+    if (variant != kTileGeneric && (a.hD + 63) / 64 <= 65535u) {
+        if (variant == kTileTma && a.vec_ok && a.d_log2 == 0) {
             bool used = false;
             const cudaError_t e = launch_tile_pass_tma(mode, interp, a, stream, &used);
             if (e != cudaSuccess || used) return e;
