@@ -36,6 +36,8 @@ struct PassArgs {
     // horizontally / vertically adjacent lattice points and between images in `src`
     uint32_t src_xstride;
     uint64_t src_pitch, src_plane;
+    // SWAR quantizer constants (quant_swar() of hgi_tile_swar.cuh, evaluated on the host per launch)
+    uint32_t q_one, q_mul, q_add, q_shift, q_scale, q_rmask, q_qmul;
 };
 
 // Dispatch of one pass.  kTileAuto: D == 1 passes on 16-byte-aligned planes go to the register-prefetch SWAR

@@ -127,7 +127,7 @@ hgi_tile_fast_kernel(const PassArgs p)
     const uint8_t* __restrict__ tile = STRIDED ? p.src + (size_t)img * p.src_plane + (size_t)Y0 * pitch + (size_t)X0 * xs
                                                : p.src + tile_off;
     const bool top = (p.c_recon == nullptr);
-    const QuantSwar qc = quant_swar(p.quant_error);
+    const QuantSwar qc = {p.q_one, p.q_mul, p.q_add, p.q_shift, p.q_scale, p.q_rmask, p.q_qmul};   // filled by the launcher
 
     // ---- 1. global loads: this thread's NU 16x2-pixel units (kept in registers for the finest level) ----
     const int sx = tid & 7, ry = tid >> 3;          // 8 column strips x RPB row pairs (x NU unit blocks)
@@ -173,7 +173,35 @@ hgi_tile_fast_kernel(const PassArgs p)
 #pragma unroll
     for (int u = 0; u < NU; ++u) stage_chunk<F>(sm.P, ev[u], 2 * ry + 2 * RPB * u, sx);
     if (halo) stage_chunk<F>(sm.P, hv, hy, hc);
-    {
+    if (NLEV == 4 && top) {
+        // top pass with step-16 seeds (src/encoder.rs:26-37 / src/decoder.rs:22-28): the seed of lattice point
+        // (16*ci, 16*cj) is byte 0 of a chunk some thread already holds; only x = TW+16 and y = TH+16 need a load
+        constexpr int pf = plane_pitch(16);
+        uint8_t* Pf = sm.P + plane_off(16);
+        uint8_t* Qf = sm.Q + plane_off(16);
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const int y = 2 * ry + 2 * RPB * u;
+            if ((y & 15) == 0) {
+                Pf[(y >> 4) * pf + sx] = (uint8_t)ev[u].x;
+                if (MODE == kModeEncode) Qf[(y >> 4) * pf + sx] = (uint8_t)ev[u].x;
+            }
+        }
+        if (halo && (hy & 15) == 0 && hy <= TH) {
+            Pf[(hy >> 4) * pf + hc] = (uint8_t)hv.x;
+            if (MODE == kModeEncode) Qf[(hy >> 4) * pf + hc] = (uint8_t)hv.x;
+        }
+        constexpr int last_ci = TW / 16 + 1, last_cj = TH / 16 + 1;
+        if (tid < last_ci + last_cj + 1) {
+            const int ci = tid <= last_cj ? last_ci : tid - (last_cj + 1);
+            const int cj = tid <= last_cj ? tid : last_cj;
+            const int x = ci * 16, y = cj * 16;
+            uint8_t rv = 0;
+            if (x < xin && y < yin) rv = __ldg(tile + (size_t)y * pitch + (size_t)x * xs);
+            Pf[cj * pf + ci] = rv;
+            if (MODE == kModeEncode) Qf[cj * pf + ci] = rv;
+        }
+    } else {
         constexpr int ncx = TW / F + 2, ncy = TH / F + 2;
         constexpr int pf = plane_pitch(F);
         uint8_t* Pf = sm.P + plane_off(F);
@@ -230,7 +258,7 @@ hgi_tile_fast_kernel(const PassArgs p)
         if (MODE == kModeEncode) qcw = *reinterpret_cast<const uint2*>(sm.Q + plane_off(2) + rp * plane_pitch(2) + 8 * sx);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t pr = pred2<INTERP>(A[k], B[k], C[k], D[k]);
+            const uint32_t pr = pred2<INTERP>(A[k], B[k], C[k], D[k], qc.one);
             const uint32_t a1 = lanes_odd(evw[k]), a2 = lanes_even(odw[k]), a3 = lanes_odd(odw[k]);
             if (MODE == kModeEncode) {
                 uint32_t r1, r2, r3;
@@ -247,8 +275,8 @@ hgi_tile_fast_kernel(const PassArgs p)
                     rec_od[k] = interleave(r2, r3);
                 }
             } else {
-                out_ev[k] = interleave(A[k], decode2(a1, pr));
-                out_od[k] = interleave(decode2(a2, pr), decode2(a3, pr));
+                out_ev[k] = interleave(A[k], decode2(a1, pr, qc.one));
+                out_od[k] = interleave(decode2(a2, pr, qc.one), decode2(a3, pr, qc.one));
             }
         }
         store_chunk<ALIGNED>(out + uoff, out_ev, row0_ok ? nvalid : 0);
@@ -319,8 +347,13 @@ cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
 }
 
 template <int MODE, int INTERP>
-cudaError_t launch_fast_t(const PassArgs& a, cudaStream_t stream)
+cudaError_t launch_fast_t(const PassArgs& args_in, cudaStream_t stream)
 {
+    PassArgs a = args_in;
+    {
+        const QuantSwar q = quant_swar(args_in.quant_error);
+        a.q_one = q.one; a.q_mul = q.mul; a.q_add = q.add; a.q_shift = q.shift; a.q_scale = q.scale; a.q_rmask = q.rmask; a.q_qmul = q.qmul;
+    }
     if (a.d_log2 > 0) {   // coarse pass: lattice view of the planes, compact outputs
         PassArgs v = a;
         v.w = a.wD;

@@ -58,7 +58,19 @@ __device__ __forceinline__ uint32_t lanes_odd(uint32_t w) { return prmt(w, 0u, 0
 // lanes (lo0, lo1), (hi0, hi1) -> bytes lo0 hi0 lo1 hi1
 __device__ __forceinline__ uint32_t interleave(uint32_t even_lanes, uint32_t odd_lanes)
 {
-    return even_lanes + (odd_lanes << 8);
+    // odd * 256 + even as ONE multiply-add: it issues on the FMA pipe, the ALU pipe is the kernel's bottleneck
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(r) : "r"(odd_lanes), "r"(even_lanes));
+    return r;
+}
+// a + b issued as a multiply-add (x * 1 + y): same result, but on the FMA pipe instead of the saturated ALU pipe
+// `one` is a register that holds 1 but is opaque to ptxas (it comes from the kernel arguments); with a literal 1
+// ptxas folds the multiply-add back into IADD3 on the ALU pipe.
+__device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, uint32_t one)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
+    return r;
 }
 __device__ __forceinline__ uint32_t avg2(uint32_t x, uint32_t y)   // src/interpolator.rs:44 per lane
 {
@@ -72,17 +84,18 @@ __device__ __forceinline__ uint32_t avg2(uint32_t x, uint32_t y)   // src/interp
 // three parity tests true -> the w).  Checked against the four-average form in tests/test_swar_model.py.
 // 8 ALU-pipe operations per register (two cells) instead of 16.
 template <int INTERP>
-__device__ __forceinline__ uint32_t pred2(uint32_t A, uint32_t B, uint32_t C, uint32_t D)
+__device__ __forceinline__ uint32_t pred2(uint32_t A, uint32_t B, uint32_t C, uint32_t D, uint32_t one)
 {
     if (INTERP == kInterpLeftTop) return A;                                    // src/interpolator.rs:26
     const uint32_t x1 = (A ^ B) & 0x00010001u;
     const uint32_t w = x1 & (C ^ D) & (A ^ C);
-    const uint32_t h = ((A + B + C) + (D + 0x00010001u)) >> 1;                 // lanes <= 510 (+ stray bit 15)
-    return ((h + w) >> 1) & M16;                                               // :51
+    const uint32_t h = fadd(fadd(A, B, one), fadd(C, D + 0x00010001u, one), one) >> 1;   // lanes <= 510 (+ stray bit 15)
+    return (fadd(h, w, one) >> 1) & M16;                                       // :51
 }
 
 // Linear quantizer as an exact per-lane multiply-shift: ((d + e) / scale) * scale for d in 0..255.
 struct QuantSwar {
+    uint32_t one;           // the constant 1, opaque to the compiler (see fadd)
     uint32_t mul, add, shift, scale;
     uint32_t rmask, qmul;   // q = umulhi(t & rmask, qmul): rmask = 0xF << shift per lane, qmul = scale << (32 - shift)
 };
@@ -94,6 +107,7 @@ __host__ __device__ inline QuantSwar quant_swar(uint32_t error)
     else if (error == 20) { k = 25; c = 0; n = 10; }
     else if (error == 30) { k = 67; c = 67; n = 12; }
     QuantSwar q;
+    q.one = 1;
     q.mul = k;
     q.add = (error * k + c) * 0x00010001u;
     q.shift = n;
@@ -107,7 +121,7 @@ __host__ __device__ inline QuantSwar quant_swar(uint32_t error)
 template <bool IDENTITY>
 __device__ __forceinline__ uint32_t encode2(uint32_t a, uint32_t p, uint32_t pk, const QuantSwar& qc, uint32_t& recon)
 {
-    const uint32_t dd = a + pk;                       // pk = 0x01000100 - p: per lane a + 256 - p, bit 8 = [a >= p]
+    const uint32_t dd = fadd(a, pk, qc.one);                  // pk = 0x01000100 - p: per lane a + 256 - p, bit 8 = [a >= p]
     const uint32_t d = dd & M16;                      // :53 wrapping_sub
     if (IDENTITY) {
         recon = a;                                    // p + (a - p) == a
@@ -117,7 +131,7 @@ __device__ __forceinline__ uint32_t encode2(uint32_t a, uint32_t p, uint32_t pk,
     // r = t >> shift per lane, q = r * scale -- done as one high multiply on the masked quotient bits, which
     // moves the shift off the ALU pipe: ((r << n) * (scale << (32 - n))) >> 32 == r * scale in both lanes
     uint32_t q = __umulhi(t & qc.rmask, qc.qmul);     // :54 table[d]
-    const uint32_t ov = q + p;                        // bit 8 = overflow                      (:56)
+    const uint32_t ov = fadd(q, p, qc.one);                   // bit 8 = overflow                      (:56)
     // overflow_is_expected = [a < p] = !bit8(dd)  =>  mismatch iff bit8(ov) == bit8(dd)       (:57-58)
     const uint32_t x = ~(ov ^ dd) & 0x01000100u;
     const uint32_t m = __umulhi(x, 0xFF000000u);      // (x * 255) >> 8: 0x00FF in every mismatching lane
@@ -126,7 +140,7 @@ __device__ __forceinline__ uint32_t encode2(uint32_t a, uint32_t p, uint32_t pk,
     return q;
 }
 
-__device__ __forceinline__ uint32_t decode2(uint32_t g, uint32_t p) { return (p + g) & M16; }  // src/decoder.rs:39
+__device__ __forceinline__ uint32_t decode2(uint32_t g, uint32_t p, uint32_t one) { return fadd(p, g, one) & M16; }  // src/decoder.rs:39
 
 __device__ __forceinline__ uint32_t valid_mask(int col0, int row, int xin_s, int yin_s)
 {
@@ -177,7 +191,7 @@ __device__ __forceinline__ void level_word(FastSmem& sm, int g, int cy, const Qu
     const uint32_t cwt = (uint32_t)*reinterpret_cast<const uint16_t*>(ct) | ((uint32_t)ct[2] << 16);
     const uint32_t cwb = (uint32_t)*reinterpret_cast<const uint16_t*>(ct + pc) | ((uint32_t)ct[pc + 2] << 16);
     const uint32_t A = lanes01(cwt), C = lanes12(cwt), B = lanes01(cwb), D = lanes12(cwb);
-    const uint32_t p = pred2<INTERP>(A, B, C, D);
+    const uint32_t p = pred2<INTERP>(A, B, C, D, qc.one);
     uint32_t* pev = reinterpret_cast<uint32_t*>(Ps + (2 * cy) * ps + 4 * g);
     uint32_t* pod = reinterpret_cast<uint32_t*>(Ps + (2 * cy + 1) * ps + 4 * g);
     const uint32_t ev = *pev, od = *pod;
@@ -194,9 +208,9 @@ __device__ __forceinline__ void level_word(FastSmem& sm, int g, int cy, const Qu
         *reinterpret_cast<uint32_t*>(Qs + (2 * cy) * ps + 4 * g) = interleave(QA, q1);
         *reinterpret_cast<uint32_t*>(Qs + (2 * cy + 1) * ps + 4 * g) = interleave(q2, q3);
     } else {
-        r1 = decode2(a1, p);
-        r2 = decode2(a2, p);
-        r3 = decode2(a3, p);
+        r1 = decode2(a1, p, qc.one);
+        r2 = decode2(a2, p, qc.one);
+        r3 = decode2(a3, p, qc.one);
     }
     uint32_t wev = interleave(A, r1), wod = interleave(r2, r3);
     if (edge) {   // out-of-image reconstruction must read as 0 (src/interpolator.rs:75-82)
@@ -250,7 +264,7 @@ __device__ __forceinline__ void coarse_level(FastSmem& sm, int tid, const QuantS
     constexpr int wpr = TW / (4 * S);               // SWAR words per cell row (2 cells each)
     constexpr int ncy = TH / (2 * S), ncx = TW / (2 * S);
     constexpr int nfr = (ncy + 1) + ncx;
-    const int xin_s = (xin + S - 1) / S, yin_s = (yin + S - 1) / S;
+    const int xin_s = (int)(((uint32_t)xin + S - 1) / (uint32_t)S), yin_s = (int)(((uint32_t)yin + S - 1) / (uint32_t)S);
     for (int it = tid; it < wpr * ncy; it += NT)
         level_word<MODE, INTERP, IDENTITY, S>(sm, it % wpr, it / wpr, qc, edge, xin_s, yin_s);
     for (int it = NT - 1 - tid; it < nfr; it += NT) {

@@ -217,7 +217,7 @@ hgi_tile_tma_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
             if (MODE == kModeEncode) qcw = *reinterpret_cast<const uint2*>(sm.Q + plane_off(2) + ry * plane_pitch(2) + 8 * sx);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t pr = pred2<INTERP>(A[k], B[k], C[k], D[k]);
+                const uint32_t pr = pred2<INTERP>(A[k], B[k], C[k], D[k], qc.one);
                 const uint32_t a1 = lanes_odd(evw[k]), a2 = lanes_even(odw[k]), a3 = lanes_odd(odw[k]);
                 if (MODE == kModeEncode) {
                     uint32_t r1, r2, r3;
@@ -234,8 +234,8 @@ hgi_tile_tma_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
                         rec_od[k] = interleave(r2, r3);
                     }
                 } else {
-                    out_ev[k] = interleave(A[k], decode2(a1, pr));
-                    out_od[k] = interleave(decode2(a2, pr), decode2(a3, pr));
+                    out_ev[k] = interleave(A[k], decode2(a1, pr, qc.one));
+                    out_od[k] = interleave(decode2(a2, pr, qc.one), decode2(a3, pr, qc.one));
                 }
             }
             uint8_t* __restrict__ out = (MODE == kModeEncode ? p.grid_out : p.recon_out) + tile_off;
