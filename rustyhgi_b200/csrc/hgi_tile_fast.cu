@@ -1,19 +1,23 @@
-// hgi_tile_fast.cu -- the fast fused HGI tile kernel (sm_100a): D == 1 passes on planes whose rows
-// are 16-byte aligned.  Same pass/tile/halo decomposition as hgi_tile_kernels.cu (the generic
-// kernel, which still serves D > 1 passes and unaligned planes), restructured so the ALU work per
-// pixel drops ~4x:
+// hgi_tile_fast.cu -- the fast fused HGI tile kernel (sm_100a), register-prefetch variant: the default for
+// every pass.  Same pass/tile/halo decomposition as hgi_tile_kernels.cu (the generic scalar kernel, now only
+// used for planes taller than 4 M rows and as a test cross-check), restructured so the work per pixel drops ~4x
+// (shared device code: hgi_tile_swar.cuh):
 //
-//  * every level s in {2,4,8,16} of the tile lives in its own DENSE shared-memory plane P_s
-//    (lattice-s points only, one byte each), so each level is "the finest level of a half-size
-//    image": even rows read [R a R a ...], odd rows [a a a a ...] -- natural 16-bit-lane SWAR;
-//  * a level reads its corners (and the coarser symbols) from the coarser plane P_2s / Q_2s and
-//    writes complete words into P_s / Q_s, so no separate "insert" step exists;
-//  * the finest level never touches shared memory for pixels: each thread loads its own 16x2
-//    pixels with two 128-bit global loads at kernel start (a software prefetch that is in flight
-//    while the coarse levels run), and stores finished grid / image words straight to HBM;
-//  * two pixels per 32-bit register: averages, residuals, the Linear quantizer (an exact
-//    multiply-shift, checked on the host against src/quantizator.rs:50-60 for all 256 inputs) and
-//    the overflow fix-up (src/encoder.rs:56-60) are all 16-bit-lane SWAR.
+//  * every level s in {2,4,8,16} of the tile lives in its own DENSE shared-memory plane P_s (lattice-s points
+//    only, one byte each), so each level is "the finest level of a half-size image": even rows read
+//    [R a R a ...], odd rows [a a a a ...] -- natural 16-bit-lane SWAR;
+//  * a level reads its corners (and the coarser symbols) from the coarser plane P_2s / Q_2s and writes complete
+//    words into P_s / Q_s, so no separate "insert" step exists;
+//  * the finest level never touches shared memory for pixels: each thread loads its own 16x2-pixel units with
+//    128-bit global loads at kernel start (a software prefetch that is in flight while the coarse levels run)
+//    and stores finished grid / image words straight to HBM;
+//  * two pixels per 32-bit register: predictor, residuals, the Linear quantizer (an exact multiply-shift, checked
+//    on the host against src/quantizator.rs:50-60 for all 256 inputs) and the overflow fix-up
+//    (src/encoder.rs:56-60) are all 16-bit-lane SWAR, with adds and interleaves steered to the FMA pipe because
+//    the ALU pipe (LOP3/SHF/PRMT) is the kernel's limiter;
+//  * instantiations: ALIGNED (w % 16 == 0, 16-byte bases: 128-bit accesses) or any width / base alignment
+//    (32-bit accesses, funnel-shifted when rows are not 4-byte aligned, bytes at the ragged right edge); STRIDED
+//    (a D > 1 pass as a lattice view: strided gathers in, compact planes out).
 //
 // Reference semantics: src/encoder.rs:39-71, src/decoder.rs:18-46, src/utils.rs:11-41,
 // src/interpolator.rs:15-28,41-91, src/quantizator.rs:41-74.

@@ -1,4 +1,6 @@
-// hgi_tile_kernels.cu -- fused multi-level HGI tile kernels (sm_100a).
+// hgi_tile_kernels.cu -- generic (scalar, byte-wise) fused multi-level HGI tile kernel (sm_100a) + pass dispatch.
+// The SWAR kernels (hgi_tile_fast.cu, hgi_tile_tma.cu) share this decomposition; this file keeps the plain
+// formulation that the CPU model tests/tile_model.py mirrors line by line.
 //
 // One launch ("pass") runs up to four consecutive levels of the closed loop for every 128x64
 // tile of the lattice {multiples of D}: the tile plus its right/bottom dependency halo is staged
