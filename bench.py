@@ -213,7 +213,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     frames_n = args.frames
-    ctx = hgi.Context(local_rank)
+    ctx = hgi.Context(local_rank, int(os.environ.get("HGI_BENCH_PATH", "0")))   # 0 = default path (tuning hook)
     encs = [hgi.Encoder(hgi.Crossed, hgi.Linear(hgi.QuantizationLevel(q)), LEVELS, ctx=ctx) for q in QLEVELS]
     dec = hgi.Decoder(hgi.Crossed, ctx=ctx)
 

@@ -258,16 +258,25 @@ __device__ __forceinline__ void fringe_cell(FastSmem& sm, int cx, int cy, const 
 
 // One coarse level (sub-step S >= 2) of the tile: SWAR words over the tile's own cells on the low
 // threads, the fringe cells (cell column TW/(2S), cell row TH/(2S)) on the high threads.
-template <int MODE, int INTERP, bool IDENTITY, int S>
+// Barrier over `GS` threads: the whole CTA (BAR == 0) or a named barrier shared by one warp group.
+template <int GS, int BAR>
+__device__ __forceinline__ void group_sync()
+{
+    if (BAR == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(GS) : "memory");
+}
+
+// `tid` in [0, GS) is the thread's index inside the group that runs the coarse levels (default: the whole CTA).
+template <int MODE, int INTERP, bool IDENTITY, int S, int GS = NT, int BAR = 0>
 __device__ __forceinline__ void coarse_level(FastSmem& sm, int tid, const QuantSwar& qc, bool edge, int xin, int yin)
 {
     constexpr int wpr = TW / (4 * S);               // SWAR words per cell row (2 cells each)
     constexpr int ncy = TH / (2 * S), ncx = TW / (2 * S);
     constexpr int nfr = (ncy + 1) + ncx;
     const int xin_s = (int)(((uint32_t)xin + S - 1) / (uint32_t)S), yin_s = (int)(((uint32_t)yin + S - 1) / (uint32_t)S);
-    for (int it = tid; it < wpr * ncy; it += NT)
+    for (int it = tid; it < wpr * ncy; it += GS)
         level_word<MODE, INTERP, IDENTITY, S>(sm, it % wpr, it / wpr, qc, edge, xin_s, yin_s);
-    for (int it = NT - 1 - tid; it < nfr; it += NT) {
+    for (int it = GS - 1 - tid; it < nfr; it += GS) {
         const int cx = it <= ncy ? ncx : it - (ncy + 1);
         const int cy = it <= ncy ? it : ncy;
         if (2 * cx < xin_s && 2 * cy < yin_s)
@@ -275,7 +284,7 @@ __device__ __forceinline__ void coarse_level(FastSmem& sm, int tid, const QuantS
         else
             (sm.P + plane_off(S))[(2 * cy) * plane_pitch(S) + 2 * cx] = 0;
     }
-    __syncthreads();
+    group_sync<GS, BAR>();
 }
 
 }  // namespace
