@@ -63,6 +63,18 @@ __device__ __forceinline__ uint32_t interleave(uint32_t even_lanes, uint32_t odd
     asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(r) : "r"(odd_lanes), "r"(even_lanes));
     return r;
 }
+// Low bytes of the lanes, interleaved: bytes even.l0 odd.l0 even.l1 odd.l1.  Unlike interleave() the inputs may
+// carry junk above bit 7 of each lane (9-bit sums), so the "& 0x00FF00FF" of a wrapping add costs nothing.
+__device__ __forceinline__ uint32_t pack_lo(uint32_t even_lanes, uint32_t odd_lanes)
+{
+    return prmt(even_lanes, odd_lanes, 0x6240u);
+}
+// symbols of encode2<IDENTITY>: dirty lanes when IDENTITY (-> pack_lo), clean otherwise (-> interleave on the FMA pipe)
+template <bool IDENTITY>
+__device__ __forceinline__ uint32_t pack_sym(uint32_t even_lanes, uint32_t odd_lanes)
+{
+    return IDENTITY ? pack_lo(even_lanes, odd_lanes) : interleave(even_lanes, odd_lanes);
+}
 // a + b issued as a multiply-add (x * 1 + y): same result, but on the FMA pipe instead of the saturated ALU pipe
 // `one` is a register that holds 1 but is opaque to ptxas (it comes from the kernel arguments); with a literal 1
 // ptxas folds the multiply-add back into IADD3 on the ALU pipe.
@@ -122,11 +134,11 @@ template <bool IDENTITY>
 __device__ __forceinline__ uint32_t encode2(uint32_t a, uint32_t p, uint32_t pk, const QuantSwar& qc, uint32_t& recon)
 {
     const uint32_t dd = fadd(a, pk, qc.one);                  // pk = 0x01000100 - p: per lane a + 256 - p, bit 8 = [a >= p]
-    const uint32_t d = dd & M16;                      // :53 wrapping_sub
     if (IDENTITY) {
         recon = a;                                    // p + (a - p) == a
-        return d;
+        return dd;                                    // low byte of each lane = the symbol; packed with pack_lo()
     }
+    const uint32_t d = dd & M16;                      // :53 wrapping_sub
     const uint32_t t = d * qc.mul + qc.add;           // lanes: (d + e) * k + c  < 2^16
     // r = t >> shift per lane, q = r * scale -- done as one high multiply on the masked quotient bits, which
     // moves the shift off the ALU pipe: ((r << n) * (scale << (32 - n))) >> 32 == r * scale in both lanes
@@ -140,7 +152,8 @@ __device__ __forceinline__ uint32_t encode2(uint32_t a, uint32_t p, uint32_t pk,
     return q;
 }
 
-__device__ __forceinline__ uint32_t decode2(uint32_t g, uint32_t p, uint32_t one) { return fadd(p, g, one) & M16; }  // src/decoder.rs:39
+// src/decoder.rs:39 for two pixels; the low byte of each lane is the pixel (pack with pack_lo())
+__device__ __forceinline__ uint32_t decode2(uint32_t g, uint32_t p, uint32_t one) { return fadd(p, g, one); }
 
 __device__ __forceinline__ uint32_t valid_mask(int col0, int row, int xin_s, int yin_s)
 {
@@ -205,14 +218,16 @@ __device__ __forceinline__ void level_word(FastSmem& sm, int g, int cy, const Qu
         uint8_t* Qs = sm.Q + plane_off(S);
         const uint8_t* Qc = sm.Q + plane_off(2 * S);
         const uint32_t QA = lanes01((uint32_t)*reinterpret_cast<const uint16_t*>(Qc + cy * pc + 2 * g));
-        *reinterpret_cast<uint32_t*>(Qs + (2 * cy) * ps + 4 * g) = interleave(QA, q1);
-        *reinterpret_cast<uint32_t*>(Qs + (2 * cy + 1) * ps + 4 * g) = interleave(q2, q3);
+        *reinterpret_cast<uint32_t*>(Qs + (2 * cy) * ps + 4 * g) = pack_sym<IDENTITY>(QA, q1);
+        *reinterpret_cast<uint32_t*>(Qs + (2 * cy + 1) * ps + 4 * g) = pack_sym<IDENTITY>(q2, q3);
     } else {
         r1 = decode2(a1, p, qc.one);
         r2 = decode2(a2, p, qc.one);
         r3 = decode2(a3, p, qc.one);
     }
-    uint32_t wev = interleave(A, r1), wod = interleave(r2, r3);
+    uint32_t wev, wod;
+    if (MODE == kModeEncode) { wev = interleave(A, r1); wod = interleave(r2, r3); }
+    else { wev = pack_lo(A, r1); wod = pack_lo(r2, r3); }
     if (edge) {   // out-of-image reconstruction must read as 0 (src/interpolator.rs:75-82)
         wev &= valid_mask(4 * g, 2 * cy, xin_s, yin_s);
         wod &= valid_mask(4 * g, 2 * cy + 1, xin_s, yin_s);

@@ -227,15 +227,15 @@ hgi_tile_tma_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
                     const uint32_t q3 = encode2<IDENTITY>(a3, pr, pk, qc, r3);
                     const uint32_t qw = (k < 2) ? qcw.x : qcw.y;
                     const uint32_t QA = (k & 1) ? lanes23(qw) : lanes01(qw);
-                    out_ev[k] = interleave(QA, q1);
-                    out_od[k] = interleave(q2, q3);
+                    out_ev[k] = pack_sym<IDENTITY>(QA, q1);
+                    out_od[k] = pack_sym<IDENTITY>(q2, q3);
                     if (EXTRA) {
                         rec_ev[k] = interleave(A[k], r1);
                         rec_od[k] = interleave(r2, r3);
                     }
                 } else {
-                    out_ev[k] = interleave(A[k], decode2(a1, pr, qc.one));
-                    out_od[k] = interleave(decode2(a2, pr, qc.one), decode2(a3, pr, qc.one));
+                    out_ev[k] = pack_lo(A[k], decode2(a1, pr, qc.one));
+                    out_od[k] = pack_lo(decode2(a2, pr, qc.one), decode2(a3, pr, qc.one));
                 }
             }
             uint8_t* __restrict__ out = (MODE == kModeEncode ? p.grid_out : p.recon_out) + tile_off;

@@ -85,3 +85,20 @@ def test_swar_quantizer_constants_are_exact():
             t = d * k + error * k + c
             assert t < 65536 and ((t >> n) & 15) * scale == ((d + error) // scale) * scale
             assert ((t & (0xF << n)) * (scale << (32 - n))) >> 32 == ((d + error) // scale) * scale
+
+
+def test_pack_lo_drops_the_carry_bits():
+    """pack_lo (PRMT 0x6240) keeps only the low byte of every lane, so wrapping adds need no mask."""
+    rng = np.random.default_rng(1)
+    for _ in range(2000):
+        p0, p1, g0, g1, h0, h1 = (int(v) for v in rng.integers(0, 256, 6))
+        even = (p0 + g0) | ((p1 + g1) << 16)                   # 9-bit sums in both lanes
+        odd = (p0 + h0) | ((p1 + h1) << 16)
+        b = [even & 255, odd & 255, (even >> 16) & 255, (odd >> 16) & 255]
+        packed = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24)
+        # __byte_perm(even, odd, 0x6240): result byte i = source byte selector nibble i (0-3 even, 4-7 odd)
+        src = [(even >> (8 * i)) & 255 for i in range(4)] + [(odd >> (8 * i)) & 255 for i in range(4)]
+        sel = 0x6240
+        got = sum(src[(sel >> (4 * i)) & 7] << (8 * i) for i in range(4))
+        assert got == packed
+        assert [got & 255, (got >> 16) & 255] == [(p0 + g0) & 255, (p1 + g1) & 255]
