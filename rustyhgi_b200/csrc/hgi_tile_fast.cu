@@ -118,6 +118,7 @@ hgi_tile_fast_kernel(const PassArgs p)
     __shared__ FastSmem sm;
     __shared__ uint32_t whist[(MODE == kModeEncode && EXTRA) ? NWARPS * 256 : 1];
     constexpr int F = 1 << NLEV;
+    constexpr bool DIRTY = (MODE == kModeDecode);   // decode only consumes the low byte of each predictor lane
 
     const int tid = threadIdx.x;
     const uint32_t img = blockIdx.z;
@@ -262,7 +263,7 @@ hgi_tile_fast_kernel(const PassArgs p)
         if (MODE == kModeEncode) qcw = *reinterpret_cast<const uint2*>(sm.Q + plane_off(2) + rp * plane_pitch(2) + 8 * sx);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t pr = pred2<INTERP>(A[k], B[k], C[k], D[k], qc.one);
+            const uint32_t pr = pred2<INTERP, DIRTY>(A[k], B[k], C[k], D[k], qc.one);
             const uint32_t a1 = lanes_odd(evw[k]), a2 = lanes_even(odw[k]), a3 = lanes_odd(odw[k]);
             if (MODE == kModeEncode) {
                 uint32_t r1, r2, r3;

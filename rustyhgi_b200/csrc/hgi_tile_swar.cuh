@@ -95,14 +95,17 @@ __device__ __forceinline__ uint32_t avg2(uint32_t x, uint32_t y)   // src/interp
 // (E/2 only matters when it makes T+E/2 cross a multiple of 4: T odd -> the +1; T = 2 mod 4 with all
 // three parity tests true -> the w).  Checked against the four-average form in tests/test_swar_model.py.
 // 8 ALU-pipe operations per register (two cells) instead of 16.
-template <int INTERP>
+// DIRTY: the caller only consumes the low byte of each lane (decode), so the final mask is
+// skipped and the lanes keep stray bits 14/15 (they never reach a low byte: every later sum stays below 2^16).
+template <int INTERP, bool DIRTY = false>
 __device__ __forceinline__ uint32_t pred2(uint32_t A, uint32_t B, uint32_t C, uint32_t D, uint32_t one)
 {
     if (INTERP == kInterpLeftTop) return A;                                    // src/interpolator.rs:26
     const uint32_t x1 = (A ^ B) & 0x00010001u;
     const uint32_t w = x1 & (C ^ D) & (A ^ C);
     const uint32_t h = fadd(fadd(A, B, one), fadd(C, D + 0x00010001u, one), one) >> 1;   // lanes <= 510 (+ stray bit 15)
-    return (fadd(h, w, one) >> 1) & M16;                                       // :51
+    const uint32_t r = fadd(h, w, one) >> 1;                                   // :51
+    return DIRTY ? r : (r & M16);
 }
 
 // Linear quantizer as an exact per-lane multiply-shift: ((d + e) / scale) * scale for d in 0..255.
@@ -204,11 +207,12 @@ __device__ __forceinline__ void level_word(FastSmem& sm, int g, int cy, const Qu
     const uint32_t cwt = (uint32_t)*reinterpret_cast<const uint16_t*>(ct) | ((uint32_t)ct[2] << 16);
     const uint32_t cwb = (uint32_t)*reinterpret_cast<const uint16_t*>(ct + pc) | ((uint32_t)ct[pc + 2] << 16);
     const uint32_t A = lanes01(cwt), C = lanes12(cwt), B = lanes01(cwb), D = lanes12(cwb);
-    const uint32_t p = pred2<INTERP>(A, B, C, D, qc.one);
+    constexpr bool DIRTY = (MODE == kModeDecode);   // decode only consumes the low byte of each predictor lane
+    const uint32_t p = pred2<INTERP, DIRTY>(A, B, C, D, qc.one);
     uint32_t* pev = reinterpret_cast<uint32_t*>(Ps + (2 * cy) * ps + 4 * g);
     uint32_t* pod = reinterpret_cast<uint32_t*>(Ps + (2 * cy + 1) * ps + 4 * g);
     const uint32_t ev = *pev, od = *pod;
-    const uint32_t a1 = lanes_odd(ev), a2 = lanes_even(od), a3 = lanes_odd(od);
+    const uint32_t a1 = lanes_odd(ev), a2 = lanes_even(od), a3 = lanes_odd(od);   // clean: p may be dirty, the sums must stay < 2^16
     uint32_t r1, r2, r3;
     if (MODE == kModeEncode) {
         const uint32_t pk = 0x01000100u - p;
@@ -226,8 +230,8 @@ __device__ __forceinline__ void level_word(FastSmem& sm, int g, int cy, const Qu
         r3 = decode2(a3, p, qc.one);
     }
     uint32_t wev, wod;
-    if (MODE == kModeEncode) { wev = interleave(A, r1); wod = interleave(r2, r3); }
-    else { wev = pack_lo(A, r1); wod = pack_lo(r2, r3); }
+    if (MODE == kModeDecode) { wev = pack_lo(A, r1); wod = pack_lo(r2, r3); }   // r = p + g with carry bits
+    else { wev = interleave(A, r1); wod = interleave(r2, r3); }               // encode: recon lanes are clean
     if (edge) {   // out-of-image reconstruction must read as 0 (src/interpolator.rs:75-82)
         wev &= valid_mask(4 * g, 2 * cy, xin_s, yin_s);
         wod &= valid_mask(4 * g, 2 * cy + 1, xin_s, yin_s);

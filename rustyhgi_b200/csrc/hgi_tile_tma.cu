@@ -94,6 +94,7 @@ hgi_tile_tma_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
     uint64_t* mbar = reinterpret_cast<uint64_t*>(dyn_smem + 2 * RAW_BYTES + sizeof(FastSmem));
     uint32_t* whist = reinterpret_cast<uint32_t*>(dyn_smem + 2 * RAW_BYTES + sizeof(FastSmem) + 16);
     constexpr int F = 1 << NLEV;
+    constexpr bool DIRTY = (MODE == kModeDecode);   // decode only consumes the low byte of each predictor lane
 
     const int tid = threadIdx.x;
     const int sx = tid & 7, ry = tid >> 3;          // 8 column strips x TH/2 row pairs
@@ -217,7 +218,7 @@ hgi_tile_tma_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
             if (MODE == kModeEncode) qcw = *reinterpret_cast<const uint2*>(sm.Q + plane_off(2) + ry * plane_pitch(2) + 8 * sx);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t pr = pred2<INTERP>(A[k], B[k], C[k], D[k], qc.one);
+                const uint32_t pr = pred2<INTERP, DIRTY>(A[k], B[k], C[k], D[k], qc.one);
                 const uint32_t a1 = lanes_odd(evw[k]), a2 = lanes_even(odw[k]), a3 = lanes_odd(odw[k]);
                 if (MODE == kModeEncode) {
                     uint32_t r1, r2, r3;

@@ -102,3 +102,20 @@ def test_pack_lo_drops_the_carry_bits():
         got = sum(src[(sel >> (4 * i)) & 7] << (8 * i) for i in range(4))
         assert got == packed
         assert [got & 255, (got >> 16) & 255] == [(p0 + g0) & 255, (p1 + g1) & 255]
+
+
+def test_dirty_predictor_lanes_are_harmless_for_decode():
+    """Decode skips the predictor's final mask (pred2<.., DIRTY>): the lanes then carry stray bits 14/15, which
+    must never reach a low byte nor carry into the other lane when a clean residual lane is added."""
+    rng = np.random.default_rng(7)
+    for _ in range(20000):
+        v = [int(x) for x in rng.integers(0, 256, 12)]
+        A, B, C, D = (v[i] | (v[i + 4] << 16) for i in range(4))
+        x1 = (A ^ B) & 0x00010001
+        w = x1 & (C ^ D) & (A ^ C)
+        h = ((A + B + C) + (D + 0x00010001)) >> 1
+        p_dirty = (h + w) >> 1
+        p_clean = p_dirty & M16
+        g = v[8] | (v[9] << 16)
+        r_d, r_c = (p_dirty + g) & U32, (p_clean + g) & U32
+        assert r_d < (1 << 32) and (r_d & 0x00FF00FF) == (r_c & 0x00FF00FF)
