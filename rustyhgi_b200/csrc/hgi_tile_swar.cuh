@@ -30,7 +30,7 @@ constexpr uint32_t M16 = 0x00FF00FFu;
 static_assert(TW == 128 && (TH == 64 || TH == 128) && NU >= 1 && NU * NT == TH * 4 && NT >= 128, "thread mapping assumes 128-wide tiles");
 
 // Dense level planes.  P_s holds lattice-s points of the tile + halo: columns 0..TW/s+1,
-// rows 0..TH/s+1 (the last ones are only partially needed, see need_limit).
+// rows 0..TH/s+1 (the last ones are only partially needed, see fringe_cell).
 __host__ __device__ constexpr int plane_pitch(int s) { return s == 2 ? 96 : (s == 4 ? 48 : (s == 8 ? 32 : 16)); }
 __host__ __device__ constexpr int plane_rows(int s) { return TH / s + 2; }
 __host__ __device__ constexpr int plane_bytes(int s) { return plane_rows(s) * plane_pitch(s); }
@@ -41,10 +41,8 @@ __host__ __device__ constexpr int plane_off(int s)
 }
 constexpr int PLANE_BYTES = plane_bytes(2) + plane_bytes(4) + plane_bytes(8) + plane_bytes(16);  // 4544 (TH=64) / 8704 (TH=128)
 
-__device__ __forceinline__ int need_limit(int tile_extent, int s)
-{
-    return s == 1 ? tile_extent - 1 : (s == 2 ? tile_extent : tile_extent + s);
-}
+// Highest tile-relative coordinate at which a new point of sub-step s is still needed:
+// TW-1, TW, TW+s for s = 1, 2, >= 4.  Used as compile-time constants in fringe_cell().
 
 // ---- 16-bit-lane SWAR primitives (two pixels per register) -----------------------------------
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
@@ -83,10 +81,6 @@ __device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, uint32_t one)
     uint32_t r;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
     return r;
-}
-__device__ __forceinline__ uint32_t avg2(uint32_t x, uint32_t y)   // src/interpolator.rs:44 per lane
-{
-    return ((x + y + 0x00010001u) >> 1) & M16;
 }
 // src/interpolator.rs:43-54 per lane.  With avg(x,y) = (x+y+1)>>1 = (x + y + ((x^y)&1)) / 2, the sum of the
 // four edge averages is T + E/2, T = A+B+C+D, where E counts the edges of the cycle A-B-D-C-A whose
