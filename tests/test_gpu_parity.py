@@ -189,6 +189,52 @@ def test_device_api_misaligned_bases_and_odd_widths(ctxs):
                 assert bool((t[:off] == fill).all()) and bool((t[off + size:] == fill).all())
 
 
+@pytest.mark.parametrize("path", ["tile", "tma"])
+def test_random_cases(ctxs, path):
+    """Seeded random sweep over sizes (aligned and ragged), levels, quantizers, interpolators and image
+    statistics: every byte of grid, reconstruction and decoded image must equal the oracle."""
+    rng = np.random.default_rng(20261018)
+    kinds = ("noise", "smooth", "const", "extremes", "ramp")
+    for case in range(70):
+        w = int(rng.choice([16, 32, 48, 128, 144, 160, 256, 272, 400])) if case % 2 == 0 else int(rng.integers(1, 420))
+        h = int(rng.integers(1, 300))
+        levels = int(rng.integers(0, 10))
+        q = int(rng.integers(0, 4))
+        interp = oc.INTERP_CROSSED if rng.random() < 0.8 else oc.INTERP_LEFTTOP
+        kind = kinds[case % len(kinds)]
+        if kind == "noise":
+            img = rng.integers(0, 256, (h, w)).astype(np.uint8)
+        elif kind == "smooth":
+            img = photo_like(w, h, case)
+        elif kind == "const":
+            img = np.full((h, w), int(rng.integers(0, 256)), np.uint8)
+        elif kind == "extremes":
+            img = (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8)
+        else:
+            yy, xx = np.mgrid[0:h, 0:w]
+            img = ((xx * 5 + yy * 3) & 255).astype(np.uint8)
+        check_case(ctxs[path], img, levels, q, interp=interp)
+
+
+def test_more_images_than_grid_z(ctxs):
+    """A batch larger than gridDim.z (65535) is cut into several launches of the SWAR kernel."""
+    import torch
+    n, h, w = 66000, 16, 16
+    rng = np.random.default_rng(11)
+    imgs = rng.integers(0, 256, (n, h, w)).astype(np.uint8)
+    t = torch.from_numpy(imgs).cuda()
+    enc = hgi.Encoder(hgi.Crossed, hgi.Linear(Q.High), 3, ctx=ctxs["tile"])
+    grids = enc.encode_device(t)
+    back = hgi.Decoder(hgi.Crossed, ctx=ctxs["tile"]).decode_device(3, grids)
+    torch.cuda.synchronize()
+    g = grids.cpu().numpy()
+    for i in (0, 1, 65534, 65535, 65536, n - 1):
+        want = oc.encode(imgs[i], 3, qlevel=3)
+        assert (g[i] == want).all()
+        assert (back[i].cpu().numpy() == oc.decode(want, 3)).all()
+    assert int((back.to(torch.int16) - t.to(torch.int16)).abs().max().item()) <= 30
+
+
 def test_archive_roundtrip_from_gpu_grid(ctxs):
     """`hgi test`-style flow (src/main.rs:73-120) on LENA.TIF level 4 Medium = BASELINE config 1."""
     img = get_plane("lena_tif")
