@@ -23,6 +23,15 @@ def test_cpp_host_mirror_compiles_and_links():
     assert os.path.exists(BIN)
 
 
+def test_criterion_transcription_compiles():
+    """tools/bench_criterion.cpp (the reference's benches/bench.rs against include/hgi.hpp) must keep building."""
+    out = os.path.join(ROOT, "build", "bench_criterion")
+    libdir = os.path.join(ROOT, "rustyhgi_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", out, os.path.join(ROOT, "tools", "bench_criterion.cpp"),
+                           "-L" + libdir, "-l:libhgi_b200.so", "-Wl,-rpath," + libdir])
+    assert os.path.exists(out)
+
+
 @pytest.mark.gpu
 def test_reference_unit_tests_in_cpp_on_gpu():
     build()
