@@ -135,13 +135,15 @@ hgi_tile_fast_kernel(const PassArgs p)
     const QuantSwar qc = {p.q_one, p.q_mul, p.q_add, p.q_shift, p.q_scale, p.q_rmask, p.q_qmul};   // filled by the launcher
 
     // ---- 1. global loads: this thread's NU 16x2-pixel units (kept in registers for the finest level) ----
-    const int sx = tid & 7, ry = tid >> 3;          // 8 column strips x RPB row pairs (x NU unit blocks)
+    const int sx = tid & 7, ry = tid >> 3;          // 8 column strips x RPB thread rows, NU adjacent row pairs each
     const int nvalid = max(0, min(16, xin - 16 * sx));   // in-image bytes of this thread's chunks (0 or 16 if ALIGNED)
-    const uint32_t toff = (uint32_t)(2 * ry) * p.w + (uint32_t)(16 * sx);   // tile-relative, fits 32 bits
+    // a thread's NU units are vertically adjacent row pairs (rp = NU*ry + u): the corner row between two units is
+    // unpacked once and shared (A/B measured ~3 % faster than units RPB row pairs apart)
+    const uint32_t toff = (uint32_t)(2 * NU * ry) * p.w + (uint32_t)(16 * sx);   // tile-relative, fits 32 bits
     uint4 ev[NU], od[NU];
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
-        const int y = 2 * ry + 2 * RPB * u;
+        const int y = 2 * (NU * ry + u);
         // a complete chunk may be over-read by <= 3 bytes unless it ends the very last row of the batch
         const bool last0 = (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 1 >= p.h) && (X0 + 16u * sx + 16u >= p.w);
         const bool last1 = (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 2 >= p.h) && (X0 + 16u * sx + 16u >= p.w);
@@ -150,8 +152,8 @@ hgi_tile_fast_kernel(const PassArgs p)
             ev[u] = load_chunk_strided(r0, y < yin ? nvalid : 0, xs);
             od[u] = load_chunk_strided(r0 + pitch, y + 1 < yin ? nvalid : 0, xs);
         } else {
-            ev[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * RPB * u) * p.w, y < yin ? nvalid : 0, !last0);
-            od[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * RPB * u + 1) * p.w, y + 1 < yin ? nvalid : 0, !last1);
+            ev[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * u) * p.w, y < yin ? nvalid : 0, !last0);
+            od[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * u + 1) * p.w, y + 1 < yin ? nvalid : 0, !last1);
         }
     }
 
@@ -176,7 +178,7 @@ hgi_tile_fast_kernel(const PassArgs p)
 
     // ---- 2. stage the dense coarse planes + the coarse lattice of this pass ---------------------
 #pragma unroll
-    for (int u = 0; u < NU; ++u) stage_chunk<F>(sm.P, ev[u], 2 * ry + 2 * RPB * u, sx);
+    for (int u = 0; u < NU; ++u) stage_chunk<F>(sm.P, ev[u], 2 * (NU * ry + u), sx);
     if (halo) stage_chunk<F>(sm.P, hv, hy, hc);
     if (NLEV == 4 && top) {
         // top pass with step-16 seeds (src/encoder.rs:26-37 / src/decoder.rs:22-28): the seed of lattice point
@@ -186,7 +188,7 @@ hgi_tile_fast_kernel(const PassArgs p)
         uint8_t* Qf = sm.Q + plane_off(16);
 #pragma unroll
         for (int u = 0; u < NU; ++u) {
-            const int y = 2 * ry + 2 * RPB * u;
+            const int y = 2 * (NU * ry + u);
             if ((y & 15) == 0) {
                 Pf[(y >> 4) * pf + sx] = (uint8_t)ev[u].x;
                 if (MODE == kModeEncode) Qf[(y >> 4) * pf + sx] = (uint8_t)ev[u].x;
@@ -242,20 +244,30 @@ hgi_tile_fast_kernel(const PassArgs p)
         for (int i = tid; i < NWARPS * 256; i += NT) whist[i] = 0u;
         __syncthreads();
     }
+    uint32_t A[4], B[4], C[4], D[4];
+    {
+        const uint8_t* P2r = sm.P + plane_off(2) + (NU * ry) * plane_pitch(2) + 8 * sx;
+        const uint2 ctw = *reinterpret_cast<const uint2*>(P2r);
+        const uint32_t cte = P2r[8];
+        A[0] = lanes01(ctw.x); A[1] = lanes23(ctw.x); A[2] = lanes01(ctw.y); A[3] = lanes23(ctw.y);
+        C[0] = lanes12(ctw.x); C[1] = __funnelshift_r(A[1], A[2], 16); C[2] = lanes12(ctw.y); C[3] = __funnelshift_r(A[3], cte, 16);
+    }
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
-        const int rp = ry + RPB * u;                // row pair (cell row) of this unit
+        const int rp = NU * ry + u;
         const bool row0_ok = 2 * rp < yin, row1_ok = 2 * rp + 1 < yin;
-        const uint32_t uoff = toff + (uint32_t)(2 * RPB * u) * p.w;
-        const uint8_t* P2r = sm.P + plane_off(2) + rp * plane_pitch(2) + 8 * sx;
-        const uint2 ctw = *reinterpret_cast<const uint2*>(P2r);
-        const uint2 cbw = *reinterpret_cast<const uint2*>(P2r + plane_pitch(2));
-        const uint32_t cte = P2r[8], cbe = P2r[plane_pitch(2) + 8];
-        uint32_t A[4], B[4], C[4], D[4];
-        A[0] = lanes01(ctw.x); A[1] = lanes23(ctw.x); A[2] = lanes01(ctw.y); A[3] = lanes23(ctw.y);
-        B[0] = lanes01(cbw.x); B[1] = lanes23(cbw.x); B[2] = lanes01(cbw.y); B[3] = lanes23(cbw.y);
-        C[0] = lanes12(ctw.x); C[1] = __funnelshift_r(A[1], A[2], 16); C[2] = lanes12(ctw.y); C[3] = __funnelshift_r(A[3], cte, 16);
-        D[0] = lanes12(cbw.x); D[1] = __funnelshift_r(B[1], B[2], 16); D[2] = lanes12(cbw.y); D[3] = __funnelshift_r(B[3], cbe, 16);
+        const uint32_t uoff = toff + (uint32_t)(2 * u) * p.w;
+        if (u > 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { A[k] = B[k]; C[k] = D[k]; }
+        }
+        {
+            const uint8_t* P2r = sm.P + plane_off(2) + (rp + 1) * plane_pitch(2) + 8 * sx;
+            const uint2 cbw = *reinterpret_cast<const uint2*>(P2r);
+            const uint32_t cbe = P2r[8];
+            B[0] = lanes01(cbw.x); B[1] = lanes23(cbw.x); B[2] = lanes01(cbw.y); B[3] = lanes23(cbw.y);
+            D[0] = lanes12(cbw.x); D[1] = __funnelshift_r(B[1], B[2], 16); D[2] = lanes12(cbw.y); D[3] = __funnelshift_r(B[3], cbe, 16);
+        }
         const uint32_t evw[4] = {ev[u].x, ev[u].y, ev[u].z, ev[u].w};
         const uint32_t odw[4] = {od[u].x, od[u].y, od[u].z, od[u].w};
         uint32_t out_ev[4], out_od[4], rec_ev[4], rec_od[4];
