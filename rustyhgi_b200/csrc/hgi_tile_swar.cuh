@@ -143,7 +143,7 @@ __device__ __forceinline__ uint32_t encode2(uint32_t a, uint32_t p, uint32_t pk,
     const uint32_t ov = fadd(q, p, qc.one);                   // bit 8 = overflow                      (:56)
     // overflow_is_expected = [a < p] = !bit8(dd)  =>  mismatch iff bit8(ov) == bit8(dd)       (:57-58)
     const uint32_t x = ~(ov ^ dd) & 0x01000100u;
-    const uint32_t m = __umulhi(x, 0xFF000000u);      // (x * 255) >> 8: 0x00FF in every mismatching lane
+    const uint32_t m = x - (x >> 8);                  // 0x00FF in every mismatching lane (A/B: the shift beats umulhi(x, 0xFF<<24) here)
     q = (q & ~m) | (d & m);                           // :59
     recon = ((ov & ~m) | (a & m)) & M16;              // :63 (p + q) mod 256, == a after a fix-up
     return q;

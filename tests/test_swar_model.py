@@ -50,7 +50,7 @@ def swar_encode2(a, p, error):
     q = ((t & rmask) * (scale << (32 - n))) >> 32             # __umulhi
     ov = (q + p) & U32
     x = (~(ov ^ dd)) & 0x01000100
-    m = (x * 0xFF000000) >> 32                                # __umulhi: 0x00FF per mismatching lane
+    m = (x - (x >> 8)) & U32                                  # 0x00FF per mismatching lane
     q = (q & ~m & U32) | (d & m)
     recon = ((ov & ~m) | (a & m)) & M16
     return q, recon
