@@ -30,6 +30,13 @@ def test_library_exports_every_declared_symbol():
     assert sorted(hgi._lib.PROTOTYPES) == names
 
 
+def test_rust_sys_crate_lists_every_symbol():
+    """bindings/rust/hgi-sys (source only, no Rust toolchain here) must stay a complete transcription of hgi.h."""
+    text = open(os.path.join(ROOT, "bindings", "rust", "hgi-sys", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (hgi_[a-z0-9_]+)\s*\(", text))
+    assert bound == set(declared_functions())
+
+
 def test_library_has_sm100a_kernels_only():
     import subprocess
     out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", hgi.LIB_PATH], capture_output=True, text=True)
