@@ -151,8 +151,7 @@ inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
 // mode: hgi::kModeEncode / kModeDecode.  All pointers are device pointers.
 int run_tile_path(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images, uint32_t w, uint32_t h,
-                  uint32_t levels, const hgi_params_t* prm, uint8_t* grid_out, uint8_t* recon_out,
-                  uint32_t* hist, cudaStream_t st)
+                  uint32_t levels, const hgi_params_t* prm, uint8_t* grid_out, uint8_t* recon_out, cudaStream_t st)
 {
     const std::vector<Pass> passes = plan_passes(levels);
     const uint32_t qerr = (mode == hgi::kModeEncode) ? hgi::level_error(prm->quant_kind, prm->quant_level) : 0u;
@@ -195,7 +194,6 @@ int run_tile_path(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images,
         if (ps.d_log2 == 0) {
             a.grid_out = grid_out;
             a.recon_out = recon_out;
-            a.hist = hist;
             a.vec_ok = (w % 16 == 0) && aligned16(src) && (grid_out == nullptr || aligned16(grid_out)) &&
                        (recon_out == nullptr || aligned16(recon_out));
         } else {
@@ -273,8 +271,8 @@ int run_dev(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images, uint3
     if (n_images == 0 || plane == 0) return HGI_OK;
     const uint32_t levels = effective_levels(prm->levels, w, h);
     uint8_t* primary = (mode == hgi::kModeEncode) ? grid_out : recon_out;
-    bool hist_done = false;
-    if (hist) HGI_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)n_images * 256 * sizeof(uint32_t), st));
+    // The residual histogram is a separate pass over the finished grid (hgi_hist_kernel): fusing the per-byte
+    // shared-memory atomics into the ALU-bound encode kernel measured slower than this pass (profiles/).
     if (levels == 0) {
         // L = 0: grid == image (src/encoder.rs:26-37 copies every pixel, the level loop is empty)
         HGI_CUDA(ctx, cudaMemcpyAsync(primary, src, (size_t)n_images * plane, cudaMemcpyDeviceToDevice, st));
@@ -284,11 +282,10 @@ int run_dev(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images, uint3
         int rc = run_level_path(ctx, mode, src, n_images, w, h, levels, prm, grid_out, recon_out, st);
         if (rc) return rc;
     } else {
-        int rc = run_tile_path(ctx, mode, src, n_images, w, h, levels, prm, grid_out, recon_out, hist, st);
+        int rc = run_tile_path(ctx, mode, src, n_images, w, h, levels, prm, grid_out, recon_out, st);
         if (rc) return rc;
-        hist_done = true;
     }
-    if (hist && !hist_done) {
+    if (hist) {
         HGI_CUDA(ctx, hgi::launch_histogram(grid_out, plane, n_images, hist, st));
         ctx->launches++;
     }

@@ -22,7 +22,6 @@ struct PassArgs {
     const uint8_t* c_q;      // compact symbols of the coarser pass (encode, non-top)
     uint8_t* s_recon;        // D>1: compact reconstruction written by this pass (wD x hD)
     uint8_t* s_q;            // D>1, encode: compact symbols written by this pass
-    uint32_t* hist;          // D==1, encode, optional: [n_images][256] (pre-zeroed)
     uint32_t w, h;           // full-resolution plane size
     uint32_t wD, hD;         // lattice size of this pass: ceil(w/D), ceil(h/D)
     uint32_t cw, ch;         // size of the coarser pass's compact planes

@@ -11,17 +11,27 @@ namespace hgi {
 namespace {
 
 constexpr int HT = 256;
-constexpr int HWARPS = HT / 32;
 
-// Each block owns a contiguous slice of one image; warps count into private shared-memory bins
-// (no inter-warp contention), then one global atomic per non-empty bin per block.
+// Each block owns a contiguous slice of one image.  Bins live in shared memory as lane-private columns,
+// cell(bin, lane) = bins[bin * 32 + lane], so the 32 lanes of a warp always hit 32 different banks: every
+// shared-memory atomic is one conflict-free wavefront whatever the symbol statistics (a residual plane is mostly
+// zeros, the worst case for per-warp bins).  The eight warps of the block share the columns; a final pass sums
+// each bin over its 32 lanes with warp shuffles and issues one global atomic per non-empty bin per block.
+__device__ __forceinline__ void hist_count_word(uint32_t* col, uint32_t w)
+{
+    atomicAdd(col + ((w & 0xFFu) << 5), 1u);
+    atomicAdd(col + ((w >> 3) & 0x1FE0u), 1u);      // ((w >> 8) & 0xFF) << 5
+    atomicAdd(col + ((w >> 11) & 0x1FE0u), 1u);     // ((w >> 16) & 0xFF) << 5
+    atomicAdd(col + ((w >> 19) & 0x1FE0u), 1u);     // (w >> 24) << 5
+}
+
 __global__ void __launch_bounds__(HT)
 hgi_hist_kernel(const uint8_t* __restrict__ data, size_t n_per_image, uint32_t blocks_per_image,
                 uint32_t* __restrict__ hist)
 {
-    __shared__ uint32_t whist[HWARPS * 256];
-    const int tid = threadIdx.x;
-    for (int i = tid; i < HWARPS * 256; i += HT) whist[i] = 0u;
+    __shared__ uint32_t bins[256 * 32];             // 32 KB
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < 256 * 32; i += HT) bins[i] = 0u;
     __syncthreads();
     const uint32_t img = blockIdx.x / blocks_per_image;
     const uint32_t b = blockIdx.x - img * blocks_per_image;
@@ -29,33 +39,35 @@ hgi_hist_kernel(const uint8_t* __restrict__ data, size_t n_per_image, uint32_t b
     const size_t per_block = ((n_per_image + blocks_per_image - 1) / blocks_per_image + 15) & ~(size_t)15;
     size_t lo = (size_t)b * per_block, hi = lo + per_block;
     if (hi > n_per_image) hi = n_per_image;
-    uint32_t* mine = &whist[(tid >> 5) * 256];
+    uint32_t* col = bins + lane;
     if (lo < hi) {
         // head up to 16 B alignment, 128-bit body, byte tail
         size_t head = ((16 - ((uintptr_t)(base + lo) & 15)) & 15);
         if (head > hi - lo) head = hi - lo;
-        for (size_t i = lo + tid; i < lo + head; i += HT) atomicAdd(&mine[base[i]], 1u);
+        for (size_t i = lo + tid; i < lo + head; i += HT) atomicAdd(col + ((uint32_t)base[i] << 5), 1u);
         const size_t vlo = lo + head;
         const size_t nvec = (hi - vlo) / 16;
         const uint4* v4 = reinterpret_cast<const uint4*>(base + vlo);
-        for (size_t i = tid; i < nvec; i += HT) {
-            const uint4 v = __ldg(v4 + i);
-            const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                atomicAdd(&mine[wds[k] & 0xFFu], 1u);
-                atomicAdd(&mine[(wds[k] >> 8) & 0xFFu], 1u);
-                atomicAdd(&mine[(wds[k] >> 16) & 0xFFu], 1u);
-                atomicAdd(&mine[wds[k] >> 24], 1u);
-            }
+        size_t i = tid;
+        for (; i + HT < nvec; i += 2 * HT) {        // two loads in flight per thread
+            const uint4 v0 = __ldg(v4 + i), v1 = __ldg(v4 + i + HT);
+            hist_count_word(col, v0.x); hist_count_word(col, v0.y); hist_count_word(col, v0.z); hist_count_word(col, v0.w);
+            hist_count_word(col, v1.x); hist_count_word(col, v1.y); hist_count_word(col, v1.z); hist_count_word(col, v1.w);
         }
-        for (size_t i = vlo + nvec * 16 + tid; i < hi; i += HT) atomicAdd(&mine[base[i]], 1u);
+        for (; i < nvec; i += HT) {
+            const uint4 v = __ldg(v4 + i);
+            hist_count_word(col, v.x); hist_count_word(col, v.y); hist_count_word(col, v.z); hist_count_word(col, v.w);
+        }
+        for (size_t j = vlo + nvec * 16 + tid; j < hi; j += HT) atomicAdd(col + ((uint32_t)base[j] << 5), 1u);
     }
     __syncthreads();
-    uint32_t total = 0;
+    // warp w reduces bins [32w, 32w+32): lane-parallel reads of one bin row, shuffle tree
+    for (int bin = (tid >> 5) * 32; bin < (tid >> 5) * 32 + 32; ++bin) {
+        uint32_t v = bins[bin * 32 + lane];
 #pragma unroll
-    for (int w = 0; w < HWARPS; ++w) total += whist[w * 256 + tid];
-    if (total) atomicAdd(&hist[(size_t)img * 256 + tid], total);
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if (lane == 0 && v) atomicAdd(&hist[(size_t)img * 256 + bin], v);
+    }
 }
 
 __global__ void __launch_bounds__(256)

@@ -15,6 +15,7 @@
 //    on the host against src/quantizator.rs:50-60 for all 256 inputs) and the overflow fix-up
 //    (src/encoder.rs:56-60) are all 16-bit-lane SWAR, with adds and interleaves steered to the FMA pipe because
 //    the ALU pipe (LOP3/SHF/PRMT) is the kernel's limiter;
+//  * EXTRA instantiations also write the reconstruction plane;
 //  * instantiations: ALIGNED (w % 16 == 0, 16-byte bases: 128-bit accesses) or any width / base alignment
 //    (32-bit accesses, funnel-shifted when rows are not 4-byte aligned, bytes at the ragged right edge); STRIDED
 //    (a D > 1 pass as a lattice view: strided gathers in, compact planes out).
@@ -116,7 +117,6 @@ __global__ void __launch_bounds__(NT, HGI_FAST_MIN_BLOCKS)
 hgi_tile_fast_kernel(const PassArgs p)
 {
     __shared__ FastSmem sm;
-    __shared__ uint32_t whist[(MODE == kModeEncode && EXTRA) ? NWARPS * 256 : 1];
     constexpr int F = 1 << NLEV;
     constexpr bool DIRTY = (MODE == kModeDecode);   // decode only consumes the low byte of each predictor lane
 
@@ -240,10 +240,6 @@ hgi_tile_fast_kernel(const PassArgs p)
 
     // ---- 4. finest level: registers + P_2 / Q_2 -> HBM -------------------------------------------
     uint8_t* __restrict__ out = (MODE == kModeEncode ? p.grid_out : p.recon_out) + tile_off;
-    if (MODE == kModeEncode && EXTRA && p.hist != nullptr) {
-        for (int i = tid; i < NWARPS * 256; i += NT) whist[i] = 0u;
-        __syncthreads();
-    }
     uint32_t A[4], B[4], C[4], D[4];
     {
         const uint8_t* P2r = sm.P + plane_off(2) + (NU * ry) * plane_pitch(2) + 8 * sx;
@@ -304,28 +300,6 @@ hgi_tile_fast_kernel(const PassArgs p)
                 store_chunk<ALIGNED>(rout + uoff, rec_ev, row0_ok ? nvalid : 0);
                 store_chunk<ALIGNED>(rout + uoff + p.w, rec_od, row1_ok ? nvalid : 0);
             }
-            // residual histogram (north_star's archive.rs stage): warp-private shared-memory bins
-            if (p.hist != nullptr && nvalid > 0) {
-                uint32_t* mine = &whist[(tid >> 5) * 256];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        if (4 * k + b >= nvalid) continue;
-                        if (row0_ok) atomicAdd(&mine[(out_ev[k] >> (8 * b)) & 0xFFu], 1u);
-                        if (row1_ok) atomicAdd(&mine[(out_od[k] >> (8 * b)) & 0xFFu], 1u);
-                    }
-                }
-            }
-        }
-    }
-    if (MODE == kModeEncode && EXTRA && p.hist != nullptr) {   // one global atomic per non-empty bin per tile
-        __syncthreads();
-        for (int bin = tid; bin < 256; bin += NT) {
-            uint32_t total = 0;
-#pragma unroll
-            for (int wv = 0; wv < NWARPS; ++wv) total += whist[wv * 256 + bin];
-            if (total) atomicAdd(&p.hist[(size_t)img * 256 + bin], total);
         }
     }
 }
@@ -343,14 +317,13 @@ cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
         a.src = args.src + (size_t)first * (STRIDED ? (size_t)args.src_plane : plane);
         if (args.grid_out) a.grid_out = args.grid_out + (size_t)first * plane;
         if (args.recon_out) a.recon_out = args.recon_out + (size_t)first * plane;
-        if (args.hist) a.hist = args.hist + (size_t)first * 256;
         if (args.c_recon) a.c_recon = args.c_recon + (size_t)first * args.cw * args.ch;
         if (args.c_q) a.c_q = args.c_q + (size_t)first * args.cw * args.ch;
         const dim3 nb(tiles_x, tiles_y, a.n_images);
         if (MODE == kModeDecode) {
             hgi_tile_fast_kernel<kModeDecode, INTERP, true, false, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a);
         } else {
-            const bool extra = (a.recon_out != nullptr) || (a.hist != nullptr);
+            const bool extra = (a.recon_out != nullptr);
             const bool ident = (a.quant_error == 0);
             if (ident && !extra) hgi_tile_fast_kernel<kModeEncode, INTERP, true, false, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a);
             else if (ident) hgi_tile_fast_kernel<kModeEncode, INTERP, true, true, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a);
@@ -380,7 +353,6 @@ cudaError_t launch_fast_t(const PassArgs& args_in, cudaStream_t stream)
         v.src_plane = (uint64_t)a.w * a.h;
         v.grid_out = a.s_q;
         v.recon_out = a.s_recon;
-        v.hist = nullptr;
         v.vec_ok = 0;
         switch (a.nlev) {
             case 1: return launch_fast_n<MODE, INTERP, 1, false, true>(v, stream);

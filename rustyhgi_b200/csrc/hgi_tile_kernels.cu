@@ -82,7 +82,6 @@ __global__ void __launch_bounds__(NT)
 hgi_tile_kernel(const PassArgs p)
 {
     __shared__ TileSmem sm;
-    __shared__ uint32_t whist[MODE == kModeEncode ? NWARPS * 256 : 1];
 
     const int tid = threadIdx.x;
     const uint32_t tiles_per_image = p.tiles_x * p.tiles_y;
@@ -184,26 +183,6 @@ hgi_tile_kernel(const PassArgs p)
                 if (MODE == kModeEncode) gout[off] = sm.Q[r * TW + x];
                 if (rout) rout[off] = sm.R[r * RPITCH + x];
             }
-        }
-        // Residual histogram of the tile (north_star's archive.rs stage; no reference code):
-        // warp-private shared-memory bins, one global atomic per non-empty bin per tile.
-        if (MODE == kModeEncode && p.hist != nullptr) {
-            for (int i = tid; i < NWARPS * 256; i += NT) whist[i] = 0u;
-            __syncthreads();
-            uint32_t* mine = &whist[(tid >> 5) * 256];
-            for (int it = tid; it < TH * (TW / 4); it += NT) {
-                const int r = it / (TW / 4), c4 = it - r * (TW / 4);
-                if (r >= yout) continue;
-                const uint32_t v = *reinterpret_cast<const uint32_t*>(&sm.Q[r * TW + 4 * c4]);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (4 * c4 + k < xout) atomicAdd(&mine[(v >> (8 * k)) & 0xFFu], 1u);
-            }
-            __syncthreads();
-            uint32_t total = 0;
-#pragma unroll
-            for (int wv = 0; wv < NWARPS; ++wv) total += whist[wv * 256 + tid];
-            if (total) atomicAdd(&p.hist[(size_t)img * 256 + tid], total);
         }
     } else {
         // compact planes for the next (finer) pass

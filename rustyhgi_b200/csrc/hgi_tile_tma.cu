@@ -45,7 +45,6 @@ static_assert(RAW_BYTES % 128 == 0 && RAW_ROW4_OFF % 128 == 0, "TMA destinations
 #ifndef HGI_TMA_MIN_BLOCKS
 #define HGI_TMA_MIN_BLOCKS (HGI_TMA_TILE_H == 128 ? 3 : 6)
 #endif
-constexpr int HWARPS = 8;   // shared-memory histogram copies (warps map onto them modulo 8)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -92,7 +91,6 @@ hgi_tile_tma_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
     uint8_t (*raw)[RAW_BYTES] = reinterpret_cast<uint8_t (*)[RAW_BYTES]>(dyn_smem);
     FastSmem& sm = *reinterpret_cast<FastSmem*>(dyn_smem + 2 * RAW_BYTES);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(dyn_smem + 2 * RAW_BYTES + sizeof(FastSmem));
-    uint32_t* whist = reinterpret_cast<uint32_t*>(dyn_smem + 2 * RAW_BYTES + sizeof(FastSmem) + 16);
     constexpr int F = 1 << NLEV;
     constexpr bool DIRTY = (MODE == kModeDecode);   // decode only consumes the low byte of each predictor lane
 
@@ -192,10 +190,6 @@ hgi_tile_tma_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
         if (F >= 4) coarse_level<MODE, INTERP, IDENTITY, 2>(sm, tid, qc, edge, xin, yin);
 
         // ---- finest level: staged pixels + P_2 / Q_2 -> HBM -----------------------------------------
-        if (MODE == kModeEncode && EXTRA && p.hist != nullptr) {
-            for (int i = tid; i < HWARPS * 256; i += NT) whist[i] = 0u;
-            __syncthreads();
-        }
         {
             const bool col_ok = 16 * sx < xin;
             const bool row0_ok = 2 * ry < yin, row1_ok = 2 * ry + 1 < yin;
@@ -248,29 +242,9 @@ hgi_tile_tma_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
                     if (col_ok && row0_ok) *reinterpret_cast<uint4*>(rout + toff) = make_uint4(rec_ev[0], rec_ev[1], rec_ev[2], rec_ev[3]);
                     if (col_ok && row1_ok) *reinterpret_cast<uint4*>(rout + toff + p.w) = make_uint4(rec_od[0], rec_od[1], rec_od[2], rec_od[3]);
                 }
-                if (p.hist != nullptr && col_ok) {   // residual histogram: warp-private shared-memory bins
-                    uint32_t* mine = &whist[((tid >> 5) & (HWARPS - 1)) * 256];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            if (row0_ok) atomicAdd(&mine[(out_ev[k] >> (8 * b)) & 0xFFu], 1u);
-                            if (row1_ok) atomicAdd(&mine[(out_od[k] >> (8 * b)) & 0xFFu], 1u);
-                        }
-                    }
-                }
             }
         }
-        __syncthreads();   // the tile is done: planes, this stage of the ring and the bins may be reused
-        if (MODE == kModeEncode && EXTRA && p.hist != nullptr) {
-            if (tid < 256) {
-                uint32_t total = 0;
-#pragma unroll
-                for (int wv = 0; wv < HWARPS; ++wv) total += whist[wv * 256 + tid];
-                if (total) atomicAdd(&p.hist[(size_t)img * 256 + tid], total);
-            }
-            __syncthreads();
-        }
+        __syncthreads();   // the tile is done: planes, this stage of the ring may be reused
         {   // advance (img, ty, tx) by gridDim.x tiles (mixed-radix add with carries)
             txx += d_tx;
             uint32_t cy = 0;
@@ -332,7 +306,7 @@ int resident_ctas()
     return n;
 }
 
-constexpr size_t smem_bytes(bool hist) { return 2 * RAW_BYTES + sizeof(FastSmem) + 16 + (hist ? HWARPS * 256 * 4 : 0); }
+constexpr size_t smem_bytes(bool) { return 2 * RAW_BYTES + sizeof(FastSmem) + 16; }
 
 template <class K>
 cudaError_t launch_one(K kernel, bool hist, uint32_t grid, cudaStream_t stream, const CUtensorMap& tm_main,
@@ -364,7 +338,7 @@ cudaError_t launch_tma_n(const PassArgs& a, cudaStream_t stream, bool* used)
     const uint32_t grid = total < (uint32_t)resident_ctas() ? total : (uint32_t)resident_ctas();
     if (MODE == kModeDecode)
         return launch_one(hgi_tile_tma_kernel<kModeDecode, INTERP, true, false, NLEV>, false, grid, stream, tm_main, tm_row, a, tiles_x, per_img, total);
-    const bool extra = (a.recon_out != nullptr) || (a.hist != nullptr);
+    const bool extra = (a.recon_out != nullptr);
     const bool ident = (a.quant_error == 0);
     if (ident && !extra)
         return launch_one(hgi_tile_tma_kernel<kModeEncode, INTERP, true, false, NLEV>, false, grid, stream, tm_main, tm_row, a, tiles_x, per_img, total);
