@@ -143,9 +143,11 @@ __device__ __forceinline__ uint32_t encode2(uint32_t a, uint32_t p, uint32_t pk,
     const uint32_t ov = fadd(q, p, qc.one);                   // bit 8 = overflow                      (:56)
     // overflow_is_expected = [a < p] = !bit8(dd)  =>  mismatch iff bit8(ov) == bit8(dd)       (:57-58)
     const uint32_t x = ~(ov ^ dd) & 0x01000100u;
-    const uint32_t m = x - (x >> 8);                  // 0x00FF in every mismatching lane (A/B: the shift beats umulhi(x, 0xFF<<24) here)
-    q = (q & ~m) | (d & m);                           // :59
-    recon = ((ov & ~m) | (a & m)) & M16;              // :63 (p + q) mod 256, == a after a fix-up
+    const uint32_t m = x - (x >> 8);                  // 0x00FF in every mismatching lane (A/B: no slower than umulhi(x, 0xFF<<24))
+    q = (q & ~m) | (dd & m);                          // :59 (m only covers the low byte of a lane, so dd's flag bit drops out: one LOP3)
+    // :63 (p + q) mod 256.  p + d == a (mod 256) and, once the fix-up has run, a + (q - d) stays inside 0..255
+    // (that is exactly what the overflow test guards), so the lanes need neither a borrow nor a mask.
+    recon = a + q - d;
     return q;
 }
 
@@ -249,9 +251,14 @@ __device__ __forceinline__ void fringe_cell(FastSmem& sm, int cx, int cy, const 
     Ps[y0 * ps + x0] = (uint8_t)A;   // the coarser lattice point itself (already 0 when out of image)
     const int px[3] = {x0 + 1, x0, x0 + 1};
     const int py[3] = {y0, y0 + 1, y0 + 1};
+    // At S == 2 the finest level only reads column TW/2 and row TH/2 of this plane: a cell of the fringe column
+    // contributes its (x0, y0+1) point, a cell of the fringe row its (x0+1, y0) point, nothing else.
+    constexpr bool ONE = (S == 2);
+    constexpr int NPT = ONE ? 1 : 3;
+    const int k2 = (x0 == xlim) ? 1 : 0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int x = px[k], y = py[k];
+    for (int kk = 0; kk < NPT; ++kk) {
+        const int x = ONE ? x0 + 1 - k2 : px[kk], y = ONE ? y0 + k2 : py[kk];
         if (x > xlim || y > ylim || x >= xin_s || y >= yin_s) continue;
         uint8_t* r = &Ps[y * ps + x];
         if (MODE == kModeEncode) {

@@ -51,8 +51,8 @@ def swar_encode2(a, p, error):
     ov = (q + p) & U32
     x = (~(ov ^ dd)) & 0x01000100
     m = (x - (x >> 8)) & U32                                  # 0x00FF per mismatching lane
-    q = (q & ~m & U32) | (d & m)
-    recon = ((ov & ~m) | (a & m)) & M16
+    q = (q & ~m & U32) | (dd & m)                             # dd's flag bit lies outside m
+    recon = (a + q - d) & U32                                 # no borrow between lanes once the fix-up ran
     return q, recon
 
 
