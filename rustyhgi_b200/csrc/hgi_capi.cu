@@ -203,8 +203,9 @@ int run_tile_path(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images,
         }
         const int variant = ctx->path == HGI_PATH_TILE_GENERIC ? hgi::kTileGeneric
                             : (ctx->path == HGI_PATH_TILE_TMA ? hgi::kTileTma : hgi::kTileAuto);
+        const uint64_t before = hgi::launch_count();
         HGI_CUDA(ctx, hgi::launch_tile_pass(mode, prm->interp, a, st, variant));
-        ctx->launches++;
+        ctx->launches += hgi::launch_count() - before;
         c_recon = a.s_recon;
         c_q = a.s_q;
         cw = a.wD;

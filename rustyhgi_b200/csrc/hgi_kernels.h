@@ -28,6 +28,7 @@ struct PassArgs {
     uint32_t d_log2;         // log2(D)
     uint32_t nlev;           // levels fused in this pass (1..4); coarse step F = 2^nlev
     uint32_t tiles_x, tiles_y;
+    uint32_t fast_tx, fast_itx, fast_ity;   // fast tile kernel, split launch: tiles per row, interior tile columns / rows
     uint32_t n_images;
     uint32_t quant_error;    // 0 => identity quantizer
     uint32_t vec_ok;         // D==1 and rows are 16-byte aligned => 128-bit global accesses
@@ -44,6 +45,9 @@ struct PassArgs {
 // the persistent TMA-pipelined kernel (hgi_tile_tma.cu) for the eligible passes instead -- measured slower
 // than the prefetch kernel in round 1 (profiles/), kept as a tested alternative.
 enum TileVariant : int { kTileAuto = 0, kTileGeneric = 1, kTileTma = 2 };
+// Kernels launched so far by the calling thread's launch_* calls (for hgi_ctx_kernel_launches).
+uint64_t& launch_count();
+
 cudaError_t launch_tile_pass(int mode, int interp, const PassArgs& args, cudaStream_t stream, int variant = kTileAuto);
 cudaError_t launch_tile_pass_fast(int mode, int interp, const PassArgs& args, cudaStream_t stream);
 cudaError_t launch_tile_pass_tma(int mode, int interp, const PassArgs& args, cudaStream_t stream, bool* used);

@@ -110,22 +110,20 @@ __device__ __forceinline__ void store_chunk(uint8_t* __restrict__ ptr, const uin
     }
 }
 
-// STRIDED: a D > 1 pass -- p.w / p.h are the lattice dimensions, pixels are gathered with the src_* strides and the
-// results go to the compact planes (grid_out = symbols, recon_out = reconstruction, both with pitch p.w).
-template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED, bool STRIDED>
-__global__ void __launch_bounds__(NT, HGI_FAST_MIN_BLOCKS)
-hgi_tile_fast_kernel(const PassArgs p)
+// EDGE = false: the tile and its whole halo lie inside the image, so every extent is a compile-time constant
+// and all the in-image predicates (loads, stores, fringe cells, masks) fold away.
+template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED, bool STRIDED, bool EDGE>
+__device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint32_t tx, uint32_t ty)
 {
-    __shared__ FastSmem sm;
     constexpr int F = 1 << NLEV;
     constexpr bool DIRTY = (MODE == kModeDecode);   // decode only consumes the low byte of each predictor lane
 
     const int tid = threadIdx.x;
     const uint32_t img = blockIdx.z;
-    const uint32_t X0 = blockIdx.x * TW, Y0 = blockIdx.y * TH;
-    const int xin = (int)min((uint32_t)(TW + FMAX + 1), p.w - X0);   // in-image extent of tile + halo
-    const int yin = (int)min((uint32_t)(TH + FMAX + 1), p.h - Y0);
-    const bool edge = (xin < TW + FMAX + 1) || (yin < TH + FMAX + 1);
+    const uint32_t X0 = tx * TW, Y0 = ty * TH;
+    const int xin = EDGE ? (int)min((uint32_t)(TW + FMAX + 1), p.w - X0) : TW + FMAX + 1;   // in-image extent of tile + halo
+    const int yin = EDGE ? (int)min((uint32_t)(TH + FMAX + 1), p.h - Y0) : TH + FMAX + 1;
+    const bool edge = EDGE;
     const size_t tile_off = ((size_t)img * p.h + Y0) * p.w + X0;     // CTA-uniform; offset in the output planes
     const uint32_t xs = STRIDED ? p.src_xstride : 1u;                // source strides (bytes)
     const size_t pitch = STRIDED ? (size_t)p.src_pitch : (size_t)p.w;
@@ -145,8 +143,8 @@ hgi_tile_fast_kernel(const PassArgs p)
     for (int u = 0; u < NU; ++u) {
         const int y = 2 * (NU * ry + u);
         // a complete chunk may be over-read by <= 3 bytes unless it ends the very last row of the batch
-        const bool last0 = (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 1 >= p.h) && (X0 + 16u * sx + 16u >= p.w);
-        const bool last1 = (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 2 >= p.h) && (X0 + 16u * sx + 16u >= p.w);
+        const bool last0 = EDGE && (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 1 >= p.h) && (X0 + 16u * sx + 16u >= p.w);
+        const bool last1 = EDGE && (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 2 >= p.h) && (X0 + 16u * sx + 16u >= p.w);
         if (STRIDED) {
             const uint8_t* r0 = tile + (size_t)y * pitch + (size_t)(16 * sx) * xs;
             ev[u] = load_chunk_strided(r0, y < yin ? nvalid : 0, xs);
@@ -304,6 +302,73 @@ hgi_tile_fast_kernel(const PassArgs p)
     }
 }
 
+// STRIDED: a D > 1 pass -- p.w / p.h are the lattice dimensions, pixels are gathered with the src_* strides and the
+// results go to the compact planes (grid_out = symbols, recon_out = reconstruction, both with pitch p.w).
+template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED, bool STRIDED>
+__global__ void __launch_bounds__(NT, HGI_FAST_MIN_BLOCKS)
+hgi_tile_fast_kernel(const PassArgs p)
+{
+    __shared__ FastSmem sm;
+    // interior tiles (88 % of a 1080p plane) take the predicate-free body; only the headline instantiations of the
+    // light kernels are split this way -- the quantizing encode is split at launch level instead (below): with both
+    // bodies in one kernel its code is 43 KB and it runs 12 % slower, an instruction-cache effect
+    constexpr bool kSplit = ((MODE == kModeDecode) || IDENTITY) && ALIGNED && !STRIDED && NLEV == 4;
+    if (kSplit) {
+        const bool interior = (blockIdx.x + 1) * TW + FMAX + 1 <= p.w && (blockIdx.y + 1) * TH + FMAX + 1 <= p.h;
+        if (interior) {
+            tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, STRIDED, false>(p, sm, blockIdx.x, blockIdx.y);
+            return;
+        }
+    }
+    tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, STRIDED, true>(p, sm, blockIdx.x, blockIdx.y);
+}
+
+// The same pass as two launches: PART 1 = the interior tiles [0, fast_itx) x [0, fast_ity) with the predicate-free
+// body, PART 2 = the remaining bottom rows and right columns of tiles, enumerated along blockIdx.x.
+template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED, bool STRIDED, int PART>
+__global__ void __launch_bounds__(NT, HGI_FAST_MIN_BLOCKS)
+hgi_tile_fast_part_kernel(const PassArgs p)
+{
+    __shared__ FastSmem sm;
+    if (PART == 1) {
+        tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, STRIDED, false>(p, sm, blockIdx.x, blockIdx.y);
+    } else {
+        const uint32_t idx = blockIdx.x, nright = (p.fast_tx - p.fast_itx) * p.fast_ity;
+        uint32_t tx, ty;
+        if (idx < nright) {                 // right columns of the interior rows
+            ty = idx / (p.fast_tx - p.fast_itx);
+            tx = p.fast_itx + (idx - ty * (p.fast_tx - p.fast_itx));
+        } else {                            // complete bottom rows
+            const uint32_t j = idx - nright;
+            ty = p.fast_ity + j / p.fast_tx;
+            tx = j - (j / p.fast_tx) * p.fast_tx;
+        }
+        tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, STRIDED, true>(p, sm, tx, ty);
+    }
+}
+
+// below this many tiles (about four waves of 10 CTAs on 148 SMs) the second launch costs more than the edge predicates
+constexpr uint64_t kSplitMinTiles = 4 * 1480;
+
+template <int MODE, int INTERP, bool EXTRA, int NLEV, bool ALIGNED, bool STRIDED>
+cudaError_t launch_fast_split(PassArgs& a, uint32_t tiles_x, uint32_t tiles_y, cudaStream_t stream)
+{
+    a.fast_tx = tiles_x;
+    a.fast_itx = a.w >= (uint32_t)(FMAX + 1) ? min(tiles_x, (a.w - (FMAX + 1)) / TW) : 0u;
+    a.fast_ity = a.h >= (uint32_t)(FMAX + 1) ? min(tiles_y, (a.h - (FMAX + 1)) / TH) : 0u;
+    if (a.fast_itx == 0 || a.fast_ity == 0) a.fast_itx = a.fast_ity = 0;
+    if (a.fast_itx) {
+        const dim3 nb(a.fast_itx, a.fast_ity, a.n_images);
+        hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, STRIDED, 1><<<nb, NT, 0, stream>>>(a); ++launch_count();
+    }
+    const uint32_t nedge = tiles_x * tiles_y - a.fast_itx * a.fast_ity;
+    if (nedge) {
+        const dim3 nb(nedge, 1, a.n_images);
+        hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, STRIDED, 2><<<nb, NT, 0, stream>>>(a); ++launch_count();
+    }
+    return cudaGetLastError();
+}
+
 template <int MODE, int INTERP, int NLEV, bool ALIGNED, bool STRIDED>
 cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
 {
@@ -321,14 +386,23 @@ cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
         if (args.c_q) a.c_q = args.c_q + (size_t)first * args.cw * args.ch;
         const dim3 nb(tiles_x, tiles_y, a.n_images);
         if (MODE == kModeDecode) {
-            hgi_tile_fast_kernel<kModeDecode, INTERP, true, false, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a);
+            hgi_tile_fast_kernel<kModeDecode, INTERP, true, false, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a); ++launch_count();
         } else {
             const bool extra = (a.recon_out != nullptr);
             const bool ident = (a.quant_error == 0);
-            if (ident && !extra) hgi_tile_fast_kernel<kModeEncode, INTERP, true, false, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a);
-            else if (ident) hgi_tile_fast_kernel<kModeEncode, INTERP, true, true, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a);
-            else if (!extra) hgi_tile_fast_kernel<kModeEncode, INTERP, false, false, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a);
-            else hgi_tile_fast_kernel<kModeEncode, INTERP, false, true, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a);
+            if (ident && !extra) { hgi_tile_fast_kernel<kModeEncode, INTERP, true, false, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
+            else if (ident) { hgi_tile_fast_kernel<kModeEncode, INTERP, true, true, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
+            else if constexpr (ALIGNED && !STRIDED && NLEV == 4 && MODE == kModeEncode) {
+                if ((uint64_t)tiles_x * tiles_y * a.n_images >= kSplitMinTiles) {
+                    const cudaError_t es = extra ? launch_fast_split<kModeEncode, INTERP, true, NLEV, ALIGNED, STRIDED>(a, tiles_x, tiles_y, stream)
+                                                 : launch_fast_split<kModeEncode, INTERP, false, NLEV, ALIGNED, STRIDED>(a, tiles_x, tiles_y, stream);
+                    if (es != cudaSuccess) return es;
+                }   // small jobs: one launch, less latency
+                else if (!extra) { hgi_tile_fast_kernel<kModeEncode, INTERP, false, false, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
+                else { hgi_tile_fast_kernel<kModeEncode, INTERP, false, true, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
+            }
+            else if (!extra) { hgi_tile_fast_kernel<kModeEncode, INTERP, false, false, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
+            else { hgi_tile_fast_kernel<kModeEncode, INTERP, false, true, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
         }
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;

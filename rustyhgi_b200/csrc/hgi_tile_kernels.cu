@@ -207,10 +207,17 @@ cudaError_t launch_t(const PassArgs& a, cudaStream_t stream)
         hgi_tile_kernel<MODE, INTERP, true><<<(uint32_t)nblocks, NT, 0, stream>>>(a);
     else
         hgi_tile_kernel<kModeEncode, INTERP, false><<<(uint32_t)nblocks, NT, 0, stream>>>(a);
+    ++launch_count();
     return cudaGetLastError();
 }
 
 }  // namespace
+
+uint64_t& launch_count()
+{
+    static thread_local uint64_t n = 0;
+    return n;
+}
 
 cudaError_t launch_tile_pass(int mode, int interp, const PassArgs& a, cudaStream_t stream, int variant)
 {

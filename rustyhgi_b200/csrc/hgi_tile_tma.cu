@@ -319,7 +319,7 @@ cudaError_t launch_one(K kernel, bool hist, uint32_t grid, cudaStream_t stream, 
     // HGI_TMA_MIN_BLOCKS CTAs really are resident per SM
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    kernel<<<grid, NT, smem, stream>>>(tm_main, tm_row, a, tiles_x, per_img, total);
+    kernel<<<grid, NT, smem, stream>>>(tm_main, tm_row, a, tiles_x, per_img, total); ++launch_count();
     return cudaGetLastError();
 }
 

@@ -116,6 +116,39 @@ def test_aligned_multi_tile_planes(ctxs, path):
             check_case(ctxs[path], rnd, levels, q)
 
 
+def test_interior_and_edge_tile_split(ctxs):
+    """The SWAR kernel runs interior tiles (tile + 17-pixel halo inside the plane) through a predicate-free body --
+    a branch for the light kernels, a launch of its own for the quantizing encode once the job has >= 5920 tiles.
+    Sizes on either side of every boundary: no interior tile, one, an interior column without an interior row."""
+    ctx = ctxs["tile"]
+    for w in (144, 160, 272, 288, 400):           # 128-wide tiles: interior columns = (w - 17) // 128
+        for h in (80, 81, 82, 144, 145, 146, 210):   # 64-high tiles: interior rows = (h - 17) // 64
+            img = photo_like(w, h, seed=3 * w + h)
+            for q in (0, 2, 3):
+                check_case(ctx, img, 4, q)
+            check_case(ctx, img, 4, 1, interp=oc.INTERP_LEFTTOP)
+    dec = hgi.Decoder(hgi.Crossed, ctx=ctx)
+    for (w, h) in [(144, 81), (160, 80), (160, 81), (272, 145), (288, 146), (416, 209)]:
+        tiles = -(-w // 128) * -(-h // 64)
+        n = -(-5920 // tiles) + 3                  # enough tiles for the two-launch path
+        base = np.stack([photo_like(w, h, seed=s + w) for s in range(6)] +
+                        [np.random.default_rng(w + h).integers(0, 256, (h, w)).astype(np.uint8)])
+        imgs = base[np.arange(n) % len(base)]
+        for q in (1, 3):
+            enc = hgi.Encoder(hgi.Crossed, hgi.Linear(Q(q)), 4, ctx=ctx)
+            launches0 = ctx.kernel_launches
+            grids, hist = enc.encode_batch(imgs, want_hist=True)
+            interior = ((w - 17) // 128) * ((h - 17) // 64) > 0
+            assert ctx.kernel_launches - launches0 == (3 if interior else 2), (w, h)   # [interior +] edge + histogram
+            want = oc.encode_batch(imgs[:len(base)], 4, qlevel=q)
+            assert (grids == want[np.arange(n) % len(base)]).all(), (w, h, q)
+            assert (hist[n - 1] == np.bincount(want[(n - 1) % len(base)].reshape(-1), minlength=256)).all()
+            assert (dec.decode_batch(4, grids[-len(base):]) == oc.decode_batch(grids[-len(base):], 4)).all()
+    launches0 = ctx.kernel_launches
+    hgi.Encoder(hgi.Crossed, hgi.Linear(Q.Medium), 4, ctx=ctx).encode(imgs[0])
+    assert ctx.kernel_launches - launches0 == 1    # a small job stays one launch
+
+
 def test_batch_host_api_and_histograms(ctxs):
     ctx = ctxs["tile"]
     for (n, w, h, levels, q) in [(5, 160, 90, 4, 2), (3, 131, 77, 5, 3), (70, 256, 128, 4, 1)]:

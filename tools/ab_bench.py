@@ -16,6 +16,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rounds", type=int, default=3)
     ap.add_argument("--frames", type=int, default=2048)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("libs", nargs="+")
     a = ap.parse_args()
     libs = [l.split("=", 1) for l in a.libs]
@@ -23,15 +24,16 @@ def main():
     for _ in range(a.rounds):
         for name, path in libs:
             env = dict(os.environ, HGI_B200_LIB=os.path.abspath(path))
-            out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "10", "--no-cpu", "--no-e2e",
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(a.steps), "--no-cpu", "--no-e2e",
                                   "--frames", str(a.frames)], env=env, capture_output=True, text=True)
             line = [l for l in out.stdout.splitlines() if l.startswith("{")]
             if not line:
                 print(name, "FAILED", out.stderr[-300:])
                 continue
             d = json.loads(line[-1])
-            res[name].append({k: v["ms"] for k, v in d["roofline"]["per_kernel"].items()} | {"step": d["ms_per_step"]})
-    keys = ["step", "encode_lossless", "decode_lossless", "encode_medium", "decode_medium"]
+            res[name].append({k: v["ms"] for k, v in d["roofline"]["per_kernel"].items()} | {"step": d["ms_per_step"]}
+                             | {"sm_mhz": d.get("clocks", {}).get("sm_mhz") or 0.0})
+    keys = ["step", "encode_lossless", "decode_lossless", "encode_medium", "decode_medium", "sm_mhz"]
     print(f"{'variant':24s} " + " ".join(f"{k:>16s}" for k in keys))
     for name, runs in res.items():
         if runs:
