@@ -110,6 +110,21 @@ __device__ __forceinline__ void store_chunk(uint8_t* __restrict__ ptr, const uin
     }
 }
 
+// sm_100 addresses shared memory through the cluster window: every basic block that touches a __shared__ object
+// rebuilds its base (S2UR SR_CgaCtaId + UMOV + ULEA, 4 % of this kernel's instructions).  Passing the 32-bit shared
+// address through an empty asm makes it an ordinary value the compiler keeps in a register; the accesses still
+// compile to LDS/STS because the pointer is rebuilt with the shared->generic intrinsic.
+__device__ __forceinline__ FastSmem& opaque_smem(FastSmem& s)
+{
+#ifdef HGI_VAR_NO_OPAQUE_SMEM
+    return s;
+#else
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(&s);
+    asm volatile("" : "+r"(a));
+    return *reinterpret_cast<FastSmem*>(__cvta_shared_to_generic(a));
+#endif
+}
+
 // EDGE = false: the tile and its whole halo lie inside the image, so every extent is a compile-time constant
 // and all the in-image predicates (loads, stores, fringe cells, masks) fold away.
 template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED, bool STRIDED, bool EDGE>
@@ -308,7 +323,8 @@ template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNE
 __global__ void __launch_bounds__(NT, HGI_FAST_MIN_BLOCKS)
 hgi_tile_fast_kernel(const PassArgs p)
 {
-    __shared__ FastSmem sm;
+    __shared__ FastSmem sm_static;
+    FastSmem& sm = opaque_smem(sm_static);
     // interior tiles (88 % of a 1080p plane) take the predicate-free body; only the headline instantiations of the
     // light kernels are split this way -- the quantizing encode is split at launch level instead (below): with both
     // bodies in one kernel its code is 43 KB and it runs 12 % slower, an instruction-cache effect
@@ -329,7 +345,8 @@ template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNE
 __global__ void __launch_bounds__(NT, HGI_FAST_MIN_BLOCKS)
 hgi_tile_fast_part_kernel(const PassArgs p)
 {
-    __shared__ FastSmem sm;
+    __shared__ FastSmem sm_static;
+    FastSmem& sm = opaque_smem(sm_static);
     if (PART == 1) {
         tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, STRIDED, false>(p, sm, blockIdx.x, blockIdx.y);
     } else {
