@@ -134,6 +134,9 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     constexpr bool DIRTY = (MODE == kModeDecode);   // decode only consumes the low byte of each predictor lane
 
     const int tid = threadIdx.x;
+#ifndef HGI_VAR_NO_ASSUME
+    __builtin_assume(tid >= 0 && tid < NT);     // lets the row/column range tests of interior tiles fold
+#endif
     const uint32_t img = blockIdx.z;
     const uint32_t X0 = tx * TW, Y0 = ty * TH;
     const int xin = EDGE ? (int)min((uint32_t)(TW + FMAX + 1), p.w - X0) : TW + FMAX + 1;   // in-image extent of tile + halo
