@@ -193,8 +193,13 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     }
 
     // ---- 2. stage the dense coarse planes + the coarse lattice of this pass ---------------------
+#ifdef HGI_VAR_NO_OWN2
+    constexpr bool OWN2 = false;
+#else
+    constexpr bool OWN2 = (F >= 4) && (NU == 2);   // the s = 2 level runs from this thread's registers (level2_owner)
+#endif
 #pragma unroll
-    for (int u = 0; u < NU; ++u) stage_chunk<F>(sm.P, ev[u], 2 * (NU * ry + u), sx);
+    for (int u = 0; u < NU; ++u) stage_chunk<F, OWN2>(sm.P, ev[u], 2 * (NU * ry + u), sx);
     if (halo) stage_chunk<F>(sm.P, hv, hy, hc);
     if (NLEV == 4 && top) {
         // top pass with step-16 seeds (src/encoder.rs:26-37 / src/decoder.rs:22-28): the seed of lattice point
@@ -252,14 +257,20 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     // ---- 3. coarse levels of the pass, s = F/2 .. 2 ---------------------------------------------
     if (F >= 16) coarse_level<MODE, INTERP, IDENTITY, 8>(sm, tid, qc, edge, xin, yin);
     if (F >= 8) coarse_level<MODE, INTERP, IDENTITY, 4>(sm, tid, qc, edge, xin, yin);
-    if (F >= 4) coarse_level<MODE, INTERP, IDENTITY, 2>(sm, tid, qc, edge, xin, yin);
+    uint32_t p2e[2] = {0u, 0u}, p2o[2] = {0u, 0u}, q2e[2] = {0u, 0u}, q2o[2] = {0u, 0u};
+    if (OWN2) {
+        level2_owner<MODE, INTERP, IDENTITY>(sm, ev[0], ev[1], sx, ry, qc, edge, xin, yin, p2e, p2o, q2e, q2o);
+        coarse_level<MODE, INTERP, IDENTITY, 2, NT, 0, false>(sm, tid, qc, edge, xin, yin);   // fringe cells + barrier
+    } else if (F >= 4) {
+        coarse_level<MODE, INTERP, IDENTITY, 2>(sm, tid, qc, edge, xin, yin);
+    }
 
     // ---- 4. finest level: registers + P_2 / Q_2 -> HBM -------------------------------------------
     uint8_t* __restrict__ out = (MODE == kModeEncode ? p.grid_out : p.recon_out) + tile_off;
     uint32_t A[4], B[4], C[4], D[4];
     {
         const uint8_t* P2r = sm.P + plane_off(2) + (NU * ry) * plane_pitch(2) + 8 * sx;
-        const uint2 ctw = *reinterpret_cast<const uint2*>(P2r);
+        const uint2 ctw = OWN2 ? make_uint2(p2e[0], p2e[1]) : *reinterpret_cast<const uint2*>(P2r);
         const uint32_t cte = P2r[8];
         A[0] = lanes01(ctw.x); A[1] = lanes23(ctw.x); A[2] = lanes01(ctw.y); A[3] = lanes23(ctw.y);
         C[0] = lanes12(ctw.x); C[1] = __funnelshift_r(A[1], A[2], 16); C[2] = lanes12(ctw.y); C[3] = __funnelshift_r(A[3], cte, 16);
@@ -275,7 +286,7 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
         }
         {
             const uint8_t* P2r = sm.P + plane_off(2) + (rp + 1) * plane_pitch(2) + 8 * sx;
-            const uint2 cbw = *reinterpret_cast<const uint2*>(P2r);
+            const uint2 cbw = (OWN2 && u == 0) ? make_uint2(p2o[0], p2o[1]) : *reinterpret_cast<const uint2*>(P2r);
             const uint32_t cbe = P2r[8];
             B[0] = lanes01(cbw.x); B[1] = lanes23(cbw.x); B[2] = lanes01(cbw.y); B[3] = lanes23(cbw.y);
             D[0] = lanes12(cbw.x); D[1] = __funnelshift_r(B[1], B[2], 16); D[2] = lanes12(cbw.y); D[3] = __funnelshift_r(B[3], cbe, 16);
@@ -284,7 +295,9 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
         const uint32_t odw[4] = {od[u].x, od[u].y, od[u].z, od[u].w};
         uint32_t out_ev[4], out_od[4], rec_ev[4], rec_od[4];
         uint2 qcw = make_uint2(0u, 0u);
-        if (MODE == kModeEncode) qcw = *reinterpret_cast<const uint2*>(sm.Q + plane_off(2) + rp * plane_pitch(2) + 8 * sx);
+        if (MODE == kModeEncode)
+            qcw = OWN2 ? (u == 0 ? make_uint2(q2e[0], q2e[1]) : make_uint2(q2o[0], q2o[1]))
+                       : *reinterpret_cast<const uint2*>(sm.Q + plane_off(2) + rp * plane_pitch(2) + 8 * sx);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t pr = pred2<INTERP, DIRTY>(A[k], B[k], C[k], D[k], qc.one);

@@ -168,10 +168,11 @@ struct FastSmem {
 
 // Stage one 16-byte chunk (columns 16c..16c+15 of tile row y, y even) into the dense planes of the
 // levels that are computed in this pass (s < F).  c == 8 is the right-halo chunk (x = TW..TW+15).
-template <int F>
+// SKIP2: the chunk's owner runs the s = 2 level from its registers (level2_owner), so P_2 needs no staging.
+template <int F, bool SKIP2 = false>
 __device__ __forceinline__ void stage_chunk(uint8_t* P, const uint4 v, int y, int c)
 {
-    if (F > 2 && y <= TH) {
+    if (F > 2 && !SKIP2 && y <= TH) {
         uint8_t* row = P + plane_off(2) + (y >> 1) * plane_pitch(2);
         if (c < 8)
             *reinterpret_cast<uint2*>(row + 8 * c) = make_uint2(prmt(v.x, v.y, 0x6420u), prmt(v.z, v.w, 0x6420u));
@@ -236,6 +237,61 @@ __device__ __forceinline__ void level_word(FastSmem& sm, int g, int cy, const Qu
     *pod = wod;
 }
 
+// The s = 2 level of one thread's own strip, from registers: the thread that holds image rows 4*ry .. 4*ry+3,
+// columns 16*sx .. 16*sx+15 (r0 = row 4*ry, r1 = row 4*ry+2) owns cell row ry, words 2*sx and 2*sx+1 of the s = 2
+// plane.  Same arithmetic as level_word<.., 2>, but the pixels never visit shared memory, the two words share their
+// corner loads, and the results stay in registers for the finest level (p2e/p2o = P_2 rows 2*ry, 2*ry+1;
+// q2e/q2o = the symbols of those rows, encode only); only the reconstruction is stored, for the neighbours.
+template <int MODE, int INTERP, bool IDENTITY>
+__device__ __forceinline__ void level2_owner(FastSmem& sm, const uint4& r0, const uint4& r1, int sx, int ry,
+                                             const QuantSwar& qc, bool edge, int xin, int yin,
+                                             uint32_t (&p2e)[2], uint32_t (&p2o)[2], uint32_t (&q2e)[2], uint32_t (&q2o)[2])
+{
+    constexpr int ps = plane_pitch(2), pc = plane_pitch(4);
+    constexpr bool DIRTY = (MODE == kModeDecode);
+    const int xin_s = (int)(((uint32_t)xin + 1) / 2u), yin_s = (int)(((uint32_t)yin + 1) / 2u);
+    const uint8_t* ct = sm.P + plane_off(4) + ry * pc + 4 * sx;
+    const uint32_t ctw = *reinterpret_cast<const uint32_t*>(ct), cte = ct[4];
+    const uint32_t cbw = *reinterpret_cast<const uint32_t*>(ct + pc), cbe = ct[pc + 4];
+    uint32_t qcw = 0u;
+    if (MODE == kModeEncode) qcw = *reinterpret_cast<const uint32_t*>(sm.Q + plane_off(4) + ry * pc + 4 * sx);
+    const uint32_t evw[2] = {prmt(r0.x, r0.y, 0x6420u), prmt(r0.z, r0.w, 0x6420u)};   // lattice-2 points of row 4*ry
+    const uint32_t odw[2] = {prmt(r1.x, r1.y, 0x6420u), prmt(r1.z, r1.w, 0x6420u)};   // ... of row 4*ry+2
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const uint32_t A = k ? lanes23(ctw) : lanes01(ctw), C = k ? prmt(ctw, cte, 0x5453u) : lanes12(ctw);
+        const uint32_t B = k ? lanes23(cbw) : lanes01(cbw), D = k ? prmt(cbw, cbe, 0x5453u) : lanes12(cbw);
+        const uint32_t p = pred2<INTERP, DIRTY>(A, B, C, D, qc.one);
+        const uint32_t a1 = lanes_odd(evw[k]), a2 = lanes_even(odw[k]), a3 = lanes_odd(odw[k]);
+        uint32_t r1v, r2v, r3v;
+        if (MODE == kModeEncode) {
+            const uint32_t pk = 0x01000100u - p;
+            const uint32_t q1 = encode2<IDENTITY>(a1, p, pk, qc, r1v);
+            const uint32_t q2 = encode2<IDENTITY>(a2, p, pk, qc, r2v);
+            const uint32_t q3 = encode2<IDENTITY>(a3, p, pk, qc, r3v);
+            const uint32_t QA = k ? lanes23(qcw) : lanes01(qcw);
+            q2e[k] = pack_sym<IDENTITY>(QA, q1);
+            q2o[k] = pack_sym<IDENTITY>(q2, q3);
+        } else {
+            r1v = decode2(a1, p, qc.one);
+            r2v = decode2(a2, p, qc.one);
+            r3v = decode2(a3, p, qc.one);
+        }
+        uint32_t wev, wod;
+        if (MODE == kModeDecode) { wev = pack_lo(A, r1v); wod = pack_lo(r2v, r3v); }
+        else { wev = interleave(A, r1v); wod = interleave(r2v, r3v); }
+        if (edge) {   // out-of-image reconstruction must read as 0 (src/interpolator.rs:75-82)
+            wev &= valid_mask(8 * sx + 4 * k, 2 * ry, xin_s, yin_s);
+            wod &= valid_mask(8 * sx + 4 * k, 2 * ry + 1, xin_s, yin_s);
+        }
+        p2e[k] = wev;
+        p2o[k] = wod;
+    }
+    uint8_t* row = sm.P + plane_off(2) + (2 * ry) * ps + 8 * sx;
+    *reinterpret_cast<uint2*>(row) = make_uint2(p2e[0], p2e[1]);
+    *reinterpret_cast<uint2*>(row + ps) = make_uint2(p2o[0], p2o[1]);
+}
+
 // One fringe cell (extra cell column / row right of and below the tile) of a coarse level, scalar.
 template <int MODE, int INTERP, bool IDENTITY, int S>
 __device__ __forceinline__ void fringe_cell(FastSmem& sm, int cx, int cy, const QuantSwar& qc, int xin_s, int yin_s)
@@ -287,15 +343,17 @@ __device__ __forceinline__ void group_sync()
 }
 
 // `tid` in [0, GS) is the thread's index inside the group that runs the coarse levels (default: the whole CTA).
-template <int MODE, int INTERP, bool IDENTITY, int S, int GS = NT, int BAR = 0>
+// WORDS = false: only the fringe cells (the caller has run the tile's own cells itself, see level2_owner).
+template <int MODE, int INTERP, bool IDENTITY, int S, int GS = NT, int BAR = 0, bool WORDS = true>
 __device__ __forceinline__ void coarse_level(FastSmem& sm, int tid, const QuantSwar& qc, bool edge, int xin, int yin)
 {
     constexpr int wpr = TW / (4 * S);               // SWAR words per cell row (2 cells each)
     constexpr int ncy = TH / (2 * S), ncx = TW / (2 * S);
     constexpr int nfr = (ncy + 1) + ncx;
     const int xin_s = (int)(((uint32_t)xin + S - 1) / (uint32_t)S), yin_s = (int)(((uint32_t)yin + S - 1) / (uint32_t)S);
-    for (int it = tid; it < wpr * ncy; it += GS)
-        level_word<MODE, INTERP, IDENTITY, S>(sm, it % wpr, it / wpr, qc, edge, xin_s, yin_s);
+    if (WORDS)
+        for (int it = tid; it < wpr * ncy; it += GS)
+            level_word<MODE, INTERP, IDENTITY, S>(sm, it % wpr, it / wpr, qc, edge, xin_s, yin_s);
     for (int it = GS - 1 - tid; it < nfr; it += GS) {
         const int cx = it <= ncy ? ncx : it - (ncy + 1);
         const int cy = it <= ncy ? it : ncy;
