@@ -309,8 +309,7 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
                 const uint32_t q2 = encode2<IDENTITY>(a2, pr, pk, qc, r2);
                 const uint32_t q3 = encode2<IDENTITY>(a3, pr, pk, qc, r3);
                 const uint32_t qw = (k < 2) ? qcw.x : qcw.y;
-                const uint32_t QA = (k & 1) ? lanes23(qw) : lanes01(qw);
-                out_ev[k] = pack_sym<IDENTITY>(QA, q1);
+                out_ev[k] = pack_even_row(qw, q1, (k & 1) != 0);
                 out_od[k] = pack_sym<IDENTITY>(q2, q3);
                 if (EXTRA) {
                     rec_ev[k] = interleave(A[k], r1);

@@ -73,6 +73,13 @@ __device__ __forceinline__ uint32_t pack_sym(uint32_t even_lanes, uint32_t odd_l
 {
     return IDENTITY ? pack_lo(even_lanes, odd_lanes) : interleave(even_lanes, odd_lanes);
 }
+// Symbols of an even row: bytes [c0, q0, c1, q1] where c0/c1 are two consecutive bytes of the coarser level's symbol
+// word `qw` (bytes 0,1 or, if `hi`, bytes 2,3) and q0/q1 the low bytes of the lanes of `odd_lanes` -- one PRMT instead
+// of unpacking the coarser symbols into lanes and interleaving.
+__device__ __forceinline__ uint32_t pack_even_row(uint32_t qw, uint32_t odd_lanes, bool hi)
+{
+    return prmt(qw, odd_lanes, hi ? 0x6342u : 0x6140u);
+}
 // a + b issued as a multiply-add (x * 1 + y): same result, but on the FMA pipe instead of the saturated ALU pipe
 // `one` is a register that holds 1 but is opaque to ptxas (it comes from the kernel arguments); with a literal 1
 // ptxas folds the multiply-add back into IADD3 on the ALU pipe.
@@ -218,8 +225,8 @@ __device__ __forceinline__ void level_word(FastSmem& sm, int g, int cy, const Qu
         const uint32_t q3 = encode2<IDENTITY>(a3, p, pk, qc, r3);
         uint8_t* Qs = sm.Q + plane_off(S);
         const uint8_t* Qc = sm.Q + plane_off(2 * S);
-        const uint32_t QA = lanes01((uint32_t)*reinterpret_cast<const uint16_t*>(Qc + cy * pc + 2 * g));
-        *reinterpret_cast<uint32_t*>(Qs + (2 * cy) * ps + 4 * g) = pack_sym<IDENTITY>(QA, q1);
+        const uint32_t qcw = (uint32_t)*reinterpret_cast<const uint16_t*>(Qc + cy * pc + 2 * g);
+        *reinterpret_cast<uint32_t*>(Qs + (2 * cy) * ps + 4 * g) = pack_even_row(qcw, q1, false);
         *reinterpret_cast<uint32_t*>(Qs + (2 * cy + 1) * ps + 4 * g) = pack_sym<IDENTITY>(q2, q3);
     } else {
         r1 = decode2(a1, p, qc.one);
@@ -269,8 +276,7 @@ __device__ __forceinline__ void level2_owner(FastSmem& sm, const uint4& r0, cons
             const uint32_t q1 = encode2<IDENTITY>(a1, p, pk, qc, r1v);
             const uint32_t q2 = encode2<IDENTITY>(a2, p, pk, qc, r2v);
             const uint32_t q3 = encode2<IDENTITY>(a3, p, pk, qc, r3v);
-            const uint32_t QA = k ? lanes23(qcw) : lanes01(qcw);
-            q2e[k] = pack_sym<IDENTITY>(QA, q1);
+            q2e[k] = pack_even_row(qcw, q1, k != 0);
             q2o[k] = pack_sym<IDENTITY>(q2, q3);
         } else {
             r1v = decode2(a1, p, qc.one);

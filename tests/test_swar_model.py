@@ -119,3 +119,22 @@ def test_dirty_predictor_lanes_are_harmless_for_decode():
         g = v[8] | (v[9] << 16)
         r_d, r_c = (p_dirty + g) & U32, (p_clean + g) & U32
         assert r_d < (1 << 32) and (r_d & 0x00FF00FF) == (r_c & 0x00FF00FF)
+
+
+def byte_perm(a, b, sel):
+    src = [(a >> (8 * i)) & 255 for i in range(4)] + [(b >> (8 * i)) & 255 for i in range(4)]
+    return sum(src[(sel >> (4 * i)) & 7] << (8 * i) for i in range(4))
+
+
+def test_pack_even_row_selectors():
+    """pack_even_row: bytes [c0, q0, c1, q1] from two consecutive bytes of the coarser symbol word and the low bytes
+    of the two 16-bit lanes of the new symbols (clean lanes, or dirty ones for the identity quantizer)."""
+    rng = np.random.default_rng(3)
+    for _ in range(2000):
+        qw = int(rng.integers(0, 1 << 32))
+        q0, q1, junk0, junk1 = (int(v) for v in rng.integers(0, 256, 4))
+        for lanes in (q0 | (q1 << 16), q0 | (junk0 << 8) | (q1 << 16) | (junk1 << 24)):
+            lo = byte_perm(qw, lanes, 0x6140)
+            hi = byte_perm(qw, lanes, 0x6342)
+            assert lo == (qw & 255) | (q0 << 8) | (((qw >> 8) & 255) << 16) | (q1 << 24)
+            assert hi == ((qw >> 16) & 255) | (q0 << 8) | (((qw >> 24) & 255) << 16) | (q1 << 24)
