@@ -95,7 +95,7 @@ __device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, uint32_t one)
 //     pred = (((T + 1) >> 1) + w) >> 1,    w = (A^B) & (C^D) & (A^C) & 1
 // (E/2 only matters when it makes T+E/2 cross a multiple of 4: T odd -> the +1; T = 2 mod 4 with all
 // three parity tests true -> the w).  Checked against the four-average form in tests/test_swar_model.py.
-// 8 ALU-pipe operations per register (two cells) instead of 16.
+// 6 ALU-pipe operations per register (two cells) instead of 16.
 // DIRTY: the caller only consumes the low byte of each lane (decode), so the final mask is
 // skipped and the lanes keep stray bits 14/15 (they never reach a low byte: every later sum stays below 2^16).
 template <int INTERP, bool DIRTY = false>
@@ -104,8 +104,11 @@ __device__ __forceinline__ uint32_t pred2(uint32_t A, uint32_t B, uint32_t C, ui
     if (INTERP == kInterpLeftTop) return A;                                    // src/interpolator.rs:26
     const uint32_t x1 = (A ^ B) & 0x00010001u;
     const uint32_t w = x1 & (C ^ D) & (A ^ C);
-    const uint32_t h = fadd(fadd(A, B, one), fadd(C, D + 0x00010001u, one), one) >> 1;   // lanes <= 510 (+ stray bit 15)
-    const uint32_t r = fadd(h, w, one) >> 1;                                   // :51
+    // (((T + 1) >> 1) + w) >> 1 == (T + 1 + 2 w) >> 2: the doubling rides on the multiply-add, one shift instead of two
+    const uint32_t t1 = fadd(fadd(A, B, one), fadd(C, D + 0x00010001u, one), one);       // lanes <= 1021
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(one + one), "r"(t1));       // lanes <= 1023
+    r >>= 2;                                                                   // :51 (+ stray bits 14, 15 in lane 0)
     return DIRTY ? r : (r & M16);
 }
 

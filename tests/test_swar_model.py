@@ -19,8 +19,8 @@ def ref_pred(A, B, C, D):
 def swar_pred(A, B, C, D):                                    # pred2<Crossed>
     x1 = (A ^ B) & 0x00010001
     w = x1 & (C ^ D) & (A ^ C)
-    h = ((A + B + C) + (D + 0x00010001)) >> 1
-    return ((h + w) >> 1) & M16
+    t1 = (A + B + C) + (D + 0x00010001)                       # T + 1 per lane
+    return ((t1 + 2 * w) >> 2) & M16                          # == (((T + 1) >> 1) + w) >> 1
 
 
 def test_parity_predictor_all_low_bit_patterns_and_ranges():
@@ -105,7 +105,7 @@ def test_pack_lo_drops_the_carry_bits():
 
 
 def test_dirty_predictor_lanes_are_harmless_for_decode():
-    """Decode skips the predictor's final mask (pred2<.., DIRTY>): the lanes then carry stray bits 14/15, which
+    """Decode skips the predictor's final mask (pred2<.., DIRTY>): the lanes then carry stray bits 14/15 (lane 1's low bits after the >> 2), which
     must never reach a low byte nor carry into the other lane when a clean residual lane is added."""
     rng = np.random.default_rng(7)
     for _ in range(20000):
@@ -113,8 +113,8 @@ def test_dirty_predictor_lanes_are_harmless_for_decode():
         A, B, C, D = (v[i] | (v[i + 4] << 16) for i in range(4))
         x1 = (A ^ B) & 0x00010001
         w = x1 & (C ^ D) & (A ^ C)
-        h = ((A + B + C) + (D + 0x00010001)) >> 1
-        p_dirty = (h + w) >> 1
+        t1 = (A + B + C) + (D + 0x00010001)
+        p_dirty = (t1 + 2 * w) >> 2
         p_clean = p_dirty & M16
         g = v[8] | (v[9] << 16)
         r_d, r_c = (p_dirty + g) & U32, (p_clean + g) & U32
