@@ -253,10 +253,28 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
         }
     }
     __syncthreads();
+#ifdef HGI_VAR_STOP_AFTER   // timing experiment (tools/time_encode.py): cut the kernel after a phase, keep the HBM traffic
+#define HGI_EARLY_STORE(extra)                                                                                        \
+    {                                                                                                                 \
+        uint8_t* o_ = (MODE == kModeEncode ? p.grid_out : p.recon_out) + tile_off;                                    \
+        for (int u = 0; u < NU; ++u) {                                                                                \
+            uint4 e_ = ev[u], d_ = od[u];                                                                             \
+            e_.x ^= (extra);                                                                                          \
+            const int y_ = 2 * (NU * ry + u);                                                                         \
+            if (nvalid > 0 && y_ < yin) *reinterpret_cast<uint4*>(o_ + toff + (uint32_t)(2 * u) * p.w) = e_;          \
+            if (nvalid > 0 && y_ + 1 < yin) *reinterpret_cast<uint4*>(o_ + toff + (uint32_t)(2 * u + 1) * p.w) = d_;  \
+        }                                                                                                             \
+        return;                                                                                                       \
+    }
+    if (HGI_VAR_STOP_AFTER == 1) HGI_EARLY_STORE(sm.P[tid])
+#endif
 
     // ---- 3. coarse levels of the pass, s = F/2 .. 2 ---------------------------------------------
     if (F >= 16) coarse_level<MODE, INTERP, IDENTITY, 8>(sm, tid, qc, edge, xin, yin);
     if (F >= 8) coarse_level<MODE, INTERP, IDENTITY, 4>(sm, tid, qc, edge, xin, yin);
+#ifdef HGI_VAR_STOP_AFTER
+    if (HGI_VAR_STOP_AFTER == 2) HGI_EARLY_STORE(sm.P[plane_off(4) + tid] ^ sm.Q[plane_off(4) + tid])
+#endif
     uint32_t p2e[2] = {0u, 0u}, p2o[2] = {0u, 0u}, q2e[2] = {0u, 0u}, q2o[2] = {0u, 0u};
     if (OWN2) {
         level2_owner<MODE, INTERP, IDENTITY>(sm, ev[0], ev[1], sx, ry, qc, edge, xin, yin, p2e, p2o, q2e, q2o);
@@ -265,6 +283,9 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
         coarse_level<MODE, INTERP, IDENTITY, 2>(sm, tid, qc, edge, xin, yin);
     }
 
+#ifdef HGI_VAR_STOP_AFTER
+    if (HGI_VAR_STOP_AFTER == 3) HGI_EARLY_STORE(p2e[0] ^ p2o[1] ^ q2e[1] ^ q2o[0] ^ sm.P[plane_off(2) + tid])
+#endif
     // ---- 4. finest level: registers + P_2 / Q_2 -> HBM -------------------------------------------
     uint8_t* __restrict__ out = (MODE == kModeEncode ? p.grid_out : p.recon_out) + tile_off;
     uint32_t A[4], B[4], C[4], D[4];

@@ -153,7 +153,8 @@ __device__ __forceinline__ uint32_t encode2(uint32_t a, uint32_t p, uint32_t pk,
     const uint32_t ov = fadd(q, p, qc.one);                   // bit 8 = overflow                      (:56)
     // overflow_is_expected = [a < p] = !bit8(dd)  =>  mismatch iff bit8(ov) == bit8(dd)       (:57-58)
     const uint32_t x = ~(ov ^ dd) & 0x01000100u;
-    const uint32_t m = x - (x >> 8);                  // 0x00FF in every mismatching lane (A/B: no slower than umulhi(x, 0xFF<<24))
+    uint32_t m;                                       // 0x00FF in every mismatching lane: per-lane min(0x0100, 0x00FF),
+    asm("min.u16x2 %0, %1, %2;" : "=r"(m) : "r"(x), "r"(0x00FF00FFu));   // one VIMNMX.U16x2 instead of shift + subtract
     q = (q & ~m) | (dd & m);                          // :59 (m only covers the low byte of a lane, so dd's flag bit drops out: one LOP3)
     // :63 (p + q) mod 256.  p + d == a (mod 256) and, once the fix-up has run, a + (q - d) stays inside 0..255
     // (that is exactly what the overflow test guards), so the lanes need neither a borrow nor a mask.

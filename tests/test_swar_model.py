@@ -50,7 +50,7 @@ def swar_encode2(a, p, error):
     q = ((t & rmask) * (scale << (32 - n))) >> 32             # __umulhi
     ov = (q + p) & U32
     x = (~(ov ^ dd)) & 0x01000100
-    m = (x - (x >> 8)) & U32                                  # 0x00FF per mismatching lane
+    m = min(x & 0xFFFF, 0xFF) | (min(x >> 16, 0xFF) << 16)     # min.u16x2(x, 0x00FF00FF): 0x00FF per mismatching lane
     q = (q & ~m & U32) | (dd & m)                             # dd's flag bit lies outside m
     recon = (a + q - d) & U32                                 # no borrow between lanes once the fix-up ran
     return q, recon
