@@ -131,7 +131,7 @@ template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNE
 __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint32_t tx, uint32_t ty)
 {
     constexpr int F = 1 << NLEV;
-    constexpr bool DIRTY = (MODE == kModeDecode);   // decode only consumes the low byte of each predictor lane
+    constexpr bool DIRTY = (MODE == kModeDecode) || kDirtyEncodePred;   // no consumer needs clean predictor lanes
 
     const int tid = threadIdx.x;
 #ifndef HGI_VAR_NO_ASSUME
@@ -325,7 +325,7 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
             const uint32_t a1 = lanes_odd(evw[k]), a2 = lanes_even(odw[k]), a3 = lanes_odd(odw[k]);
             if (MODE == kModeEncode) {
                 uint32_t r1, r2, r3;
-                const uint32_t pk = 0x01000100u - pr;
+                const uint32_t pk = bias_sub(pr, qc.one);
                 const uint32_t q1 = encode2<IDENTITY>(a1, pr, pk, qc, r1);
                 const uint32_t q2 = encode2<IDENTITY>(a2, pr, pk, qc, r2);
                 const uint32_t q3 = encode2<IDENTITY>(a3, pr, pk, qc, r3);

@@ -89,6 +89,17 @@ __device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, uint32_t one)
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
     return r;
 }
+// pk for encode2: per lane 256 - p.  The predictor may keep stray bits 14/15 in lane 0 (pred2<.., DIRTY>), so the
+// subtraction must not borrow across the lanes: ~p (as p * -1 - 1 on the FMA pipe, opaque -1) plus 257 with a
+// lane-wise add (VIADD.16x2).  The strays survive in pk and dd but sit above bit 8 and below the next lane.
+constexpr bool kDirtyEncodePred = true;
+__device__ __forceinline__ uint32_t bias_sub(uint32_t p, uint32_t one)
+{
+    uint32_t np, r;
+    asm("mad.lo.u32 %0, %1, %2, %2;" : "=r"(np) : "r"(p), "r"(0u - one));
+    asm("add.u16x2 %0, %1, %2;" : "=r"(r) : "r"(np), "r"(0x01010101u));
+    return r;
+}
 // src/interpolator.rs:43-54 per lane.  With avg(x,y) = (x+y+1)>>1 = (x + y + ((x^y)&1)) / 2, the sum of the
 // four edge averages is T + E/2, T = A+B+C+D, where E counts the edges of the cycle A-B-D-C-A whose
 // endpoints differ in parity (0, 2 or 4).  Working through floor((T + E/2)/4) by the parity of T gives
@@ -215,7 +226,7 @@ __device__ __forceinline__ void level_word(FastSmem& sm, int g, int cy, const Qu
     const uint32_t cwt = (uint32_t)*reinterpret_cast<const uint16_t*>(ct) | ((uint32_t)ct[2] << 16);
     const uint32_t cwb = (uint32_t)*reinterpret_cast<const uint16_t*>(ct + pc) | ((uint32_t)ct[pc + 2] << 16);
     const uint32_t A = lanes01(cwt), C = lanes12(cwt), B = lanes01(cwb), D = lanes12(cwb);
-    constexpr bool DIRTY = (MODE == kModeDecode);   // decode only consumes the low byte of each predictor lane
+    constexpr bool DIRTY = (MODE == kModeDecode) || kDirtyEncodePred;   // no consumer needs clean predictor lanes
     const uint32_t p = pred2<INTERP, DIRTY>(A, B, C, D, qc.one);
     uint32_t* pev = reinterpret_cast<uint32_t*>(Ps + (2 * cy) * ps + 4 * g);
     uint32_t* pod = reinterpret_cast<uint32_t*>(Ps + (2 * cy + 1) * ps + 4 * g);
@@ -223,7 +234,7 @@ __device__ __forceinline__ void level_word(FastSmem& sm, int g, int cy, const Qu
     const uint32_t a1 = lanes_odd(ev), a2 = lanes_even(od), a3 = lanes_odd(od);   // clean: p may be dirty, the sums must stay < 2^16
     uint32_t r1, r2, r3;
     if (MODE == kModeEncode) {
-        const uint32_t pk = 0x01000100u - p;
+        const uint32_t pk = bias_sub(p, qc.one);
         const uint32_t q1 = encode2<IDENTITY>(a1, p, pk, qc, r1);
         const uint32_t q2 = encode2<IDENTITY>(a2, p, pk, qc, r2);
         const uint32_t q3 = encode2<IDENTITY>(a3, p, pk, qc, r3);
@@ -259,7 +270,7 @@ __device__ __forceinline__ void level2_owner(FastSmem& sm, const uint4& r0, cons
                                              uint32_t (&p2e)[2], uint32_t (&p2o)[2], uint32_t (&q2e)[2], uint32_t (&q2o)[2])
 {
     constexpr int ps = plane_pitch(2), pc = plane_pitch(4);
-    constexpr bool DIRTY = (MODE == kModeDecode);
+    constexpr bool DIRTY = (MODE == kModeDecode) || kDirtyEncodePred;
     const int xin_s = (int)(((uint32_t)xin + 1) / 2u), yin_s = (int)(((uint32_t)yin + 1) / 2u);
     const uint8_t* ct = sm.P + plane_off(4) + ry * pc + 4 * sx;
     const uint32_t ctw = *reinterpret_cast<const uint32_t*>(ct), cte = ct[4];
@@ -276,7 +287,7 @@ __device__ __forceinline__ void level2_owner(FastSmem& sm, const uint4& r0, cons
         const uint32_t a1 = lanes_odd(evw[k]), a2 = lanes_even(odw[k]), a3 = lanes_odd(odw[k]);
         uint32_t r1v, r2v, r3v;
         if (MODE == kModeEncode) {
-            const uint32_t pk = 0x01000100u - p;
+            const uint32_t pk = bias_sub(p, qc.one);
             const uint32_t q1 = encode2<IDENTITY>(a1, p, pk, qc, r1v);
             const uint32_t q2 = encode2<IDENTITY>(a2, p, pk, qc, r2v);
             const uint32_t q3 = encode2<IDENTITY>(a3, p, pk, qc, r3v);

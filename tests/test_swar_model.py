@@ -138,3 +138,22 @@ def test_pack_even_row_selectors():
             hi = byte_perm(qw, lanes, 0x6342)
             assert lo == (qw & 255) | (q0 << 8) | (((qw >> 8) & 255) << 16) | (q1 << 24)
             assert hi == ((qw >> 16) & 255) | (q0 << 8) | (((qw >> 24) & 255) << 16) | (q1 << 24)
+
+
+def test_lanewise_bias_tolerates_dirty_predictor_lanes():
+    """bias_sub: pk = ~p + 257 per 16-bit lane (mad.lo with -1, then add.u16x2).  With stray bits 14/15 in lane 0 of
+    the predictor, dd = a + pk still has the residual in its low byte, [a >= p] in bit 8, and lane 1 untouched; the
+    overflow sum q + p keeps its bit 8 too."""
+    def add16x2(x, y):
+        return ((x + y) & 0xFFFF) | ((((x >> 16) + (y >> 16)) & 0xFFFF) << 16)
+    rng = np.random.default_rng(9)
+    for _ in range(20000):
+        a0, a1, p0, p1, q0, q1 = (int(v) for v in rng.integers(0, 256, 6))
+        stray = int(rng.integers(0, 4)) << 14
+        a, p = a0 | (a1 << 16), (p0 | stray) | (p1 << 16)
+        pk = add16x2((~p) & U32, 0x01010101)
+        dd = (a + pk) & U32
+        assert (dd & 0xFF, (dd >> 16) & 0xFF) == ((a0 - p0) & 255, (a1 - p1) & 255)
+        assert ((dd >> 8) & 1, (dd >> 24) & 1) == (int(a0 >= p0), int(a1 >= p1))
+        ov = ((q0 | (q1 << 16)) + p) & U32
+        assert ((ov >> 8) & 1, (ov >> 24) & 1) == (int(q0 + p0 > 255), int(q1 + p1 > 255))
