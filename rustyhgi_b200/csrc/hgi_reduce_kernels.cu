@@ -70,14 +70,28 @@ hgi_hist_kernel(const uint8_t* __restrict__ data, size_t n_per_image, uint32_t b
     }
 }
 
+// 16 pixels per thread and iteration when both planes are 16-byte aligned: |a - b| per byte, squares summed with a
+// 4-way dot product (exact: 4 * 255^2 per word fits 32 bits, widened to 64 bits per 16 bytes), running byte-wise max.
 __global__ void __launch_bounds__(256)
 hgi_error_kernel(const uint8_t* __restrict__ before, const uint8_t* __restrict__ after, size_t n,
-                 unsigned long long* __restrict__ out2)
+                 unsigned long long* __restrict__ out2, int vec_ok)
 {
     unsigned long long sum = 0;
     uint32_t mx = 0;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t groups = vec_ok ? n / 16 : 0;
+    uint32_t mx4 = 0;
+    for (size_t g = tid; g < groups; g += stride) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(before) + g);
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(after) + g);
+        const uint32_t d0 = __vabsdiffu4(a.x, b.x), d1 = __vabsdiffu4(a.y, b.y);   // src/main.rs:89
+        const uint32_t d2 = __vabsdiffu4(a.z, b.z), d3 = __vabsdiffu4(a.w, b.w);
+        mx4 = __vmaxu4(__vmaxu4(mx4, d0), __vmaxu4(d1, __vmaxu4(d2, d3)));
+        sum += __dp4a(d0, d0, __dp4a(d1, d1, __dp4a(d2, d2, __dp4a(d3, d3, 0u))));   // src/main.rs:91
+    }
+    mx = max(max(mx4 & 255u, (mx4 >> 8) & 255u), max((mx4 >> 16) & 255u, mx4 >> 24));
+    for (size_t i = groups * 16 + tid; i < n; i += stride) {
         const int d = (int)before[i] - (int)after[i];        // src/main.rs:89
         const uint32_t a = (uint32_t)(d < 0 ? -d : d);
         mx = max(mx, a);
@@ -111,6 +125,21 @@ __device__ __forceinline__ uint32_t luma_of(uint32_t r, uint32_t g, uint32_t b)
     return (uint32_t)l;   // truncation; l < 256
 }
 
+// The same arithmetic without the conversion unit: byte `k` of word `w` becomes the float 2^23 + byte by a single
+// PRMT into the mantissa of 0x4B000000, minus 2^23 gives (float)byte exactly; the truncation is an add of 2^23
+// rounded toward zero, whose low mantissa byte is floor(l) (0 <= l < 256).  Returns that float's bits.
+__device__ __forceinline__ float byte_to_f32(uint32_t w, uint32_t k)
+{
+    return __fadd_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + k)), -8388608.0f);
+}
+__device__ __forceinline__ uint32_t luma_bits(float r, float g, float b)
+{
+    float l = __fmul_rn(0.2126f, r);
+    l = __fadd_rn(l, __fmul_rn(0.7152f, g));
+    l = __fadd_rn(l, __fmul_rn(0.0722f, b));
+    return __float_as_uint(__fadd_rz(l, 8388608.0f));   // low byte = (u8)l
+}
+
 // 16 pixels per thread: three 128-bit loads (48 RGB bytes), one 128-bit store.
 __global__ void __launch_bounds__(256)
 hgi_luma_kernel(const uint8_t* __restrict__ rgb, size_t n_pixels, uint8_t* __restrict__ luma, int vec_ok)
@@ -127,11 +156,11 @@ hgi_luma_kernel(const uint8_t* __restrict__ rgb, size_t n_pixels, uint8_t* __res
 #pragma unroll
             for (int q = 0; q < 4; ++q) {   // 4 pixels = 12 bytes = words 3q..3q+2
                 const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
-                const uint32_t l0 = luma_of(a & 255u, (a >> 8) & 255u, (a >> 16) & 255u);
-                const uint32_t l1 = luma_of(a >> 24, b & 255u, (b >> 8) & 255u);
-                const uint32_t l2 = luma_of((b >> 16) & 255u, b >> 24, c & 255u);
-                const uint32_t l3 = luma_of((c >> 8) & 255u, (c >> 16) & 255u, c >> 24);
-                out[q] = l0 | (l1 << 8) | (l2 << 16) | (l3 << 24);
+                const uint32_t l0 = luma_bits(byte_to_f32(a, 0), byte_to_f32(a, 1), byte_to_f32(a, 2));
+                const uint32_t l1 = luma_bits(byte_to_f32(a, 3), byte_to_f32(b, 0), byte_to_f32(b, 1));
+                const uint32_t l2 = luma_bits(byte_to_f32(b, 2), byte_to_f32(b, 3), byte_to_f32(c, 0));
+                const uint32_t l3 = luma_bits(byte_to_f32(c, 1), byte_to_f32(c, 2), byte_to_f32(c, 3));
+                out[q] = __byte_perm(__byte_perm(l0, l1, 0x0040u), __byte_perm(l2, l3, 0x0040u), 0x5410u);
             }
             *reinterpret_cast<uint4*>(luma + gidx * 16) = make_uint4(out[0], out[1], out[2], out[3]);
         }
@@ -173,9 +202,10 @@ cudaError_t launch_error_metrics(const uint8_t* before, const uint8_t* after, si
 {
     cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(unsigned long long), stream);
     if (e != cudaSuccess || n == 0) return e;
+    const int vec_ok = (((uintptr_t)before | (uintptr_t)after) & 15u) == 0;
     uint64_t blocks = (n + 256 * 64 - 1) / (256 * 64);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    hgi_error_kernel<<<(uint32_t)blocks, 256, 0, stream>>>(before, after, n, out2);
+    hgi_error_kernel<<<(uint32_t)blocks, 256, 0, stream>>>(before, after, n, out2, vec_ok);
     return cudaGetLastError();
 }
 
