@@ -61,14 +61,37 @@ def profiled_traffic():
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: in-process NVML every 5 ms (a thread; the main
+    thread sits in cudaDeviceSynchronize with the GIL released), `nvidia-smi -lms` as the fallback -- its piped output
+    arrives in bursts, which loses short timed regions."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+            0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.stop_flag = index, [], None, None, False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            pr = torch.cuda.get_device_properties(self.index)
+            bus = f"{pr.pci_domain_id:08X}:{pr.pci_bus_id:02X}:{pr.pci_device_id:02X}.0"
+            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
     def start(self):
+        try:
+            self.nvml = self._nvml_handle()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                           "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -77,22 +100,44 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nvml
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = 0
+        while not self.stop_flag:
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                flags = ["Active" if mask & bit else "Not Active" for bit in (0x8, 0x40, 0x20, 0x4)]
+                self.rows.append((time.time(), [str(self.index), str(clk), str(mx), "", hex(mask)] + flags))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self, t0=0.0, t1=float("inf")):
         """Summary of the samples that arrived in the host-time window [t0, t1]."""
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(5)
-        except Exception:
-            self.proc.kill()
+        self.stop_flag = True
+        if self.nvml is None and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(5)
+            except Exception:
+                self.proc.kill()
+        slack = 0.06 if self.proc else 0.0
         sm, mx, reasons = [], [], set()
         for ts, r in self.rows:
-            if not (t0 <= ts <= t1 + 0.06):
+            if not (t0 <= ts <= t1 + slack):
                 continue
             try:
                 sm.append(float(r[1]))
@@ -103,7 +148,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi", "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -364,24 +364,54 @@ __device__ __forceinline__ void group_sync()
 }
 
 // `tid` in [0, GS) is the thread's index inside the group that runs the coarse levels (default: the whole CTA).
-// WORDS = false: only the fringe cells (the caller has run the tile's own cells itself, see level2_owner).
+// The fringe (cell column TW/(2S) and cell row TH/(2S), needed by the finer levels of this tile) is computed as
+// ordinary SWAR words: word column `wpr` and cell row `ncy` extend the loop.  Their second cell / odd row reaches
+// two plane columns (one plane row) further than any consumer reads -- inside the plane pitch, computed from stale
+// bytes, never used.
+// WORDS = false: only the fringe words (the caller has run the tile's own cells itself, see level2_owner).
 template <int MODE, int INTERP, bool IDENTITY, int S, int GS = NT, int BAR = 0, bool WORDS = true>
 __device__ __forceinline__ void coarse_level(FastSmem& sm, int tid, const QuantSwar& qc, bool edge, int xin, int yin)
 {
     constexpr int wpr = TW / (4 * S);               // SWAR words per cell row (2 cells each)
     constexpr int ncy = TH / (2 * S), ncx = TW / (2 * S);
-    constexpr int nfr = (ncy + 1) + ncx;
     const int xin_s = (int)(((uint32_t)xin + S - 1) / (uint32_t)S), yin_s = (int)(((uint32_t)yin + S - 1) / (uint32_t)S);
-    if (WORDS)
-        for (int it = tid; it < wpr * ncy; it += GS)
-            level_word<MODE, INTERP, IDENTITY, S>(sm, it % wpr, it / wpr, qc, edge, xin_s, yin_s);
-    for (int it = GS - 1 - tid; it < nfr; it += GS) {
-        const int cx = it <= ncy ? ncx : it - (ncy + 1);
-        const int cy = it <= ncy ? it : ncy;
-        if (2 * cx < xin_s && 2 * cy < yin_s)
-            fringe_cell<MODE, INTERP, IDENTITY, S>(sm, cx, cy, qc, xin_s, yin_s);
-        else
-            (sm.P + plane_off(S))[(2 * cy) * plane_pitch(S) + 2 * cx] = 0;
+#ifdef HGI_VAR_SCALAR_FRINGE
+    constexpr bool kScalarFringe = true;
+#elif defined(HGI_VAR_WORD_FRINGE_ALL)
+    constexpr bool kScalarFringe = false;
+#else
+    // the identity encode's s = 2 fringe stays scalar: one point per cell without a quantizer is ~35 instructions on
+    // two warps, cheaper for that latency-bound kernel than 32 full words on one warp (A/B)
+    constexpr bool kScalarFringe = !WORDS && IDENTITY && MODE == kModeEncode;
+#endif
+    if (kScalarFringe) {
+        constexpr int nfr = (ncy + 1) + ncx;
+        if (WORDS)
+            for (int it = tid; it < wpr * ncy; it += GS)
+                level_word<MODE, INTERP, IDENTITY, S>(sm, it % wpr, it / wpr, qc, edge, xin_s, yin_s);
+        for (int it = GS - 1 - tid; it < nfr; it += GS) {
+            const int cx = it <= ncy ? ncx : it - (ncy + 1);
+            const int cy = it <= ncy ? it : ncy;
+            if (2 * cx < xin_s && 2 * cy < yin_s)
+                fringe_cell<MODE, INTERP, IDENTITY, S>(sm, cx, cy, qc, xin_s, yin_s);
+            else
+                (sm.P + plane_off(S))[(2 * cy) * plane_pitch(S) + 2 * cx] = 0;
+        }
+    } else if (WORDS) {
+        constexpr int wx = wpr + 1, nwords = wx * (ncy + 1);
+        for (int it = tid; it < nwords; it += GS) {
+            const int cy = (int)((uint32_t)it / (uint32_t)wx);
+            level_word<MODE, INTERP, IDENTITY, S>(sm, it - cy * wx, cy, qc, edge, xin_s, yin_s);
+        }
+    } else {
+        // wpr words of the fringe row (cy = ncy), then ncy words of the fringe column (g = wpr), on the highest threads
+        // (32 words = one warp at S = 2); of the corner cell only the lattice point itself is read by anyone: a copy of
+        // the coarser plane's byte (0 when out of the image)
+        constexpr int nfw = wpr + ncy;
+        for (int it = GS - 1 - tid; it < nfw; it += GS)
+            level_word<MODE, INTERP, IDENTITY, S>(sm, it < wpr ? it : wpr, it < wpr ? ncy : it - wpr, qc, edge, xin_s, yin_s);
+        if (tid == GS - 1)
+            (sm.P + plane_off(S))[(2 * ncy) * plane_pitch(S) + 4 * wpr] = (sm.P + plane_off(2 * S))[ncy * plane_pitch(2 * S) + 2 * wpr];
     }
     group_sync<GS, BAR>();
 }
