@@ -15,6 +15,13 @@
 //    on the host against src/quantizator.rs:50-60 for all 256 inputs) and the overflow fix-up
 //    (src/encoder.rs:56-60) are all 16-bit-lane SWAR, with adds and interleaves steered to the FMA pipe because
 //    the ALU pipe (LOP3/SHF/PRMT) is the kernel's limiter;
+//  * the s = 2 level is owner-computed: the thread that holds a 16x4 pixel strip runs cell row ry, words 2sx and
+//    2sx+1 of that level from its registers (level2_owner) and keeps P_2 / Q_2 of the strip for the finest level;
+//  * the fringe (the extra cell column / row a tile recomputes instead of exchanging) is one more word column and
+//    cell row of the same SWAR loop;
+//  * interior tiles (tile + halo inside the plane) run a body without any in-image predicate (EDGE = false): a
+//    branch in the light kernels, a launch of its own for the quantizing encode (instruction-cache footprint);
+//  * the shared-memory window base is pinned in a register (opaque_smem);
 //  * EXTRA instantiations also write the reconstruction plane;
 //  * instantiations: ALIGNED (w % 16 == 0, 16-byte bases: 128-bit accesses) or any width / base alignment
 //    (32-bit accesses, funnel-shifted when rows are not 4-byte aligned, bytes at the ragged right edge); STRIDED
@@ -23,8 +30,8 @@
 // Reference semantics: src/encoder.rs:39-71, src/decoder.rs:18-46, src/utils.rs:11-41,
 // src/interpolator.rs:15-28,41-91, src/quantizator.rs:41-74.
 // Tile shape / CTA size / residency of the register-prefetch kernel.  Measured on B200 (bench.py, 4096 frames,
-// ms per step): 128x64 tiles with 128 threads (2 units per thread) at 10 CTAs/SM 14.5; 128x128 / 256 / 6: 15.1;
-// 128x64 / 256 / 8: 16.0.  Small CTAs keep every barrier inside four warps.
+// ms per step, at the time of the sweep): 128x64 tiles with 128 threads (2 units per thread) at 10 CTAs/SM 14.5;
+// 128x128 / 256 / 6: 15.1; 128x64 / 256 / 8: 16.0.  Small CTAs keep every barrier inside four warps.
 #ifndef HGI_FAST_TILE_H
 #define HGI_FAST_TILE_H 64
 #endif

@@ -1,7 +1,8 @@
 // hgi_tile_swar.cuh -- shared device code of the fast HGI tile kernels (sm_100a): dense per-level plane
 // geometry, 16-bit-lane SWAR arithmetic (predictor, quantizer, fix-up), plane staging and the coarse-level
-// routines.  Included by hgi_tile_fast.cu (register-prefetch kernel, 128x128 tiles) and hgi_tile_tma.cu
-// (persistent TMA-pipelined kernel, 128x64 tiles); each defines HGI_TILE_H before including this file.
+// routines.  Included by hgi_tile_fast.cu (register-prefetch kernel, 128x64 tiles, 128 threads) and
+// hgi_tile_tma.cu (persistent TMA-pipelined kernel, 128x128 tiles, 512 threads); each defines HGI_TILE_H /
+// HGI_TILE_NT before including this file.
 //
 // Reference semantics: src/encoder.rs:39-71, src/decoder.rs:18-46, src/utils.rs:11-41,
 // src/interpolator.rs:15-28,41-91, src/quantizator.rs:41-74.
