@@ -1,6 +1,14 @@
 #!/bin/bash
 # Build a kernel variant of libhgi_b200.so for tools/ab_bench.py:  tools/build_variant.sh NAME [-DFLAG ...]
 # Recompiles the tile kernels with the extra flags into build/NAME/ and links them with the stock objects.
+# A/B hooks in the kernels (each restores the behaviour a change replaced, or cuts the kernel for timing):
+#   -DHGI_VAR_NO_OPAQUE_SMEM     shared-memory window base rebuilt in every basic block (ptxas default)
+#   -DHGI_VAR_NO_ASSUME          no __builtin_assume on the thread index
+#   -DHGI_VAR_NO_OWN2            s = 2 level through shared memory (level_word) instead of level2_owner
+#   -DHGI_VAR_SCALAR_FRINGE      fringe cells as scalar code;  -DHGI_VAR_WORD_FRINGE_ALL  as SWAR words everywhere
+#   -DHGI_FAST_MIN_BLOCKS=n / -DHGI_FAST_MIN_BLOCKS_LIGHT=n   CTAs per SM (quantizing encode / light kernels)
+#   -DHGI_FAST_TILE_H=128 -DHGI_FAST_NT=256                   tile shape / CTA size
+#   -DHGI_VAR_STOP_AFTER=1|2|3   cut after set-up / s=8,4 / s=2 and copy the pixels out (tools/time_encode.py)
 set -e
 cd "$(dirname "$0")/../rustyhgi_b200/csrc"
 name=$1; shift
