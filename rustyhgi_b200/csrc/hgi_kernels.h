@@ -38,6 +38,7 @@ struct PassArgs {
     uint64_t src_pitch, src_plane;
     // SWAR quantizer constants (quant_swar() of hgi_tile_swar.cuh, evaluated on the host per launch)
     uint32_t q_one, q_mul, q_add, q_shift, q_scale, q_rmask, q_qmul;
+    uint32_t q_hK, q_hc1, q_hS, q_hc2;   // fp16x2 form
 };
 
 // Dispatch of one pass.  kTileAuto: D == 1 passes on 16-byte-aligned planes go to the register-prefetch SWAR

@@ -143,8 +143,6 @@ template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNE
 __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint32_t tx, uint32_t ty)
 {
     constexpr int F = 1 << NLEV;
-    constexpr bool DIRTY = (MODE == kModeDecode) || kDirtyEncodePred;   // no consumer needs clean predictor lanes
-
     const int tid = threadIdx.x;
 #ifndef HGI_VAR_NO_ASSUME
     __builtin_assume(tid >= 0 && tid < NT);     // lets the row/column range tests of interior tiles fold
@@ -160,7 +158,7 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     const uint8_t* __restrict__ tile = STRIDED ? p.src + (size_t)img * p.src_plane + (size_t)Y0 * pitch + (size_t)X0 * xs
                                                : p.src + tile_off;
     const bool top = (p.c_recon == nullptr);
-    const QuantSwar qc = {p.q_one, p.q_mul, p.q_add, p.q_shift, p.q_scale, p.q_rmask, p.q_qmul};   // filled by the launcher
+    const QuantSwar qc = {p.q_one, p.q_mul, p.q_add, p.q_shift, p.q_scale, p.q_rmask, p.q_qmul, p.q_hK, p.q_hc1, p.q_hS, p.q_hc2};   // filled by the launcher
 
     // ---- 1. global loads: this thread's NU 16x2-pixel units (kept in registers for the finest level) ----
     const int sx = tid & 7, ry = tid >> 3;          // 8 column strips x RPB thread rows, NU adjacent row pairs each
@@ -333,22 +331,19 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
                        : *reinterpret_cast<const uint2*>(sm.Q + plane_off(2) + rp * plane_pitch(2) + 8 * sx);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t pr = pred2<INTERP, DIRTY>(A[k], B[k], C[k], D[k], qc.one);
             const uint32_t a1 = lanes_odd(evw[k]), a2 = lanes_even(odw[k]), a3 = lanes_odd(odw[k]);
             if (MODE == kModeEncode) {
-                uint32_t r1, r2, r3;
-                const uint32_t pk = bias_sub(pr, qc.one);
-                const uint32_t q1 = encode2<IDENTITY>(a1, pr, pk, qc, r1);
-                const uint32_t q2 = encode2<IDENTITY>(a2, pr, pk, qc, r2);
-                const uint32_t q3 = encode2<IDENTITY>(a3, pr, pk, qc, r3);
+                uint32_t q[3], r[3];
+                encode_cells<INTERP, IDENTITY>(A[k], B[k], C[k], D[k], a1, a2, a3, qc, q, r);
                 const uint32_t qw = (k < 2) ? qcw.x : qcw.y;
-                out_ev[k] = pack_even_row(qw, q1, (k & 1) != 0);
-                out_od[k] = pack_sym<IDENTITY>(q2, q3);
+                out_ev[k] = pack_even_row(qw, q[0], (k & 1) != 0);
+                out_od[k] = pack_sym<IDENTITY>(q[1], q[2]);
                 if (EXTRA) {
-                    rec_ev[k] = interleave(A[k], r1);
-                    rec_od[k] = interleave(r2, r3);
+                    rec_ev[k] = interleave(A[k], r[0]);
+                    rec_od[k] = interleave(r[1], r[2]);
                 }
             } else {
+                const uint32_t pr = pred2<INTERP, true>(A[k], B[k], C[k], D[k], qc.one);
                 out_ev[k] = pack_lo(A[k], decode2(a1, pr, qc.one));
                 out_od[k] = pack_lo(decode2(a2, pr, qc.one), decode2(a3, pr, qc.one));
             }
@@ -479,10 +474,7 @@ template <int MODE, int INTERP>
 cudaError_t launch_fast_t(const PassArgs& args_in, cudaStream_t stream)
 {
     PassArgs a = args_in;
-    {
-        const QuantSwar q = quant_swar(args_in.quant_error);
-        a.q_one = q.one; a.q_mul = q.mul; a.q_add = q.add; a.q_shift = q.shift; a.q_scale = q.scale; a.q_rmask = q.rmask; a.q_qmul = q.qmul;
-    }
+    fill_quant_args(a);
     if (a.d_log2 > 0) {   // coarse pass: lattice view of the planes, compact outputs
         PassArgs v = a;
         v.w = a.wD;

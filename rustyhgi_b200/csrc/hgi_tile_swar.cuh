@@ -101,6 +101,57 @@ __device__ __forceinline__ uint32_t bias_sub(uint32_t p, uint32_t one)
     asm("add.u16x2 %0, %1, %2;" : "=r"(r) : "r"(np), "r"(0x01010101u));
     return r;
 }
+// ---- fp16x2 arithmetic on integer lanes ------------------------------------------------------------------------
+// A 16-bit lane that holds an integer n < 2048 is, read as an fp16 bit pattern, the number n * 2^-24 (subnormals and
+// the first normal binade share the ulp 2^-24; sm_100 does not flush them).  HFMA2 therefore does exact integer
+// arithmetic on both lanes of a register with ONE rounding to the nearest integer at the end -- which turns a
+// "multiply, add, shift" (three instructions, the shift on the saturated ALU pipe) into one instruction on the FMA
+// pipe, and yields clean lanes (no bits shifted across the lane boundary).  tools/ubench_pipes.cu measures the
+// pipes (HFMA2 / IMAD: FMA pipe, 0.5 per clock; LOP3 / PRMT / SHF / VIMNMX / HSET2: ALU pipe, 0.5 per clock; IMAD.HI
+// 0.25 per clock) and checks the exactness on the device; tests/test_swar_model.py models it on the CPU.
+__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t hmul2(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+constexpr uint32_t kH_eighth = 0x30003000u;       // 0.125
+constexpr uint32_t kH_neg_eighth = 0xB000B000u;   // -0.125
+constexpr uint32_t kH_511ulp = 0x01FF01FFu;       // 511 * 2^-24
+constexpr uint32_t kH_257ulp = 0x01010101u;       // 257 * 2^-24
+constexpr uint32_t kH_255_256 = 0x3BF83BF8u;      // 255/256: 0x0100 -> 0x00FF per lane
+
+// Crossed predictor for the quantizing encode: returns pk = 256 - pred per lane and, if WANT_P, p = pred + 512 (the
+// only consumer is bit 8 of q + p; the bias keeps the lane away from -0 when pred == 0); both clean.
+// pred = (T + 1 + 2w) >> 2 (see pred2 below) = RN((2T + 4w - 1) / 8): the argument is an odd multiple of 1/8,
+// so round-to-nearest never sees a tie and equals the floor.  The lanes carry yb = 2T + 4w + 7 (<= 2047 because
+// w = 1 needs mixed parities, i.e. T <= 1018), pred + 512 = RN(yb/8 + 511) and 256 - pred = RN(257 - yb/8).
+template <int INTERP, bool WANT_P>
+__device__ __forceinline__ uint32_t pred_pk2(uint32_t A, uint32_t B, uint32_t C, uint32_t D, uint32_t one, uint32_t& p)
+{
+    if (INTERP == kInterpLeftTop) {                                            // src/interpolator.rs:26
+        p = A;
+        uint32_t pk;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(pk) : "r"(A), "r"(0u - one), "r"(0x01000100u));
+        return pk;
+    }
+    const uint32_t x1 = (A ^ B) & 0x00010001u;
+    const uint32_t w = x1 & (C ^ D) & (A ^ C);
+    uint32_t t2, yb;
+    const uint32_t t3 = A + B + C;                                             // one IADD3 (the FMA pipe carries more of this path than the ALU pipe)
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t2) : "r"(D), "r"(one + one), "r"(0x00070007u));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t2) : "r"(t3), "r"(one + one), "r"(t2));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(yb) : "r"(w), "r"(4u * one), "r"(t2));
+    if (WANT_P) p = hfma2(yb, kH_eighth, kH_511ulp);
+    return hfma2(yb, kH_neg_eighth, kH_257ulp);
+}
+
 // src/interpolator.rs:43-54 per lane.  With avg(x,y) = (x+y+1)>>1 = (x + y + ((x^y)&1)) / 2, the sum of the
 // four edge averages is T + E/2, T = A+B+C+D, where E counts the edges of the cycle A-B-D-C-A whose
 // endpoints differ in parity (0, 2 or 4).  Working through floor((T + E/2)/4) by the parity of T gives
@@ -129,8 +180,33 @@ struct QuantSwar {
     uint32_t one;           // the constant 1, opaque to the compiler (see fadd)
     uint32_t mul, add, shift, scale;
     uint32_t rmask, qmul;   // q = umulhi(t & rmask, qmul): rmask = 0xF << shift per lane, qmul = scale << (32 - shift)
+    // fp16x2 form (both lanes): r = d * hK + hc1 = base + floor((d + e) / scale) * ulp(base), q = r * hS + hc2
+    uint32_t hK, hc1, hS, hc2;
 };
-__host__ __device__ inline QuantSwar quant_swar(uint32_t error)
+// double -> fp16 bits, round to nearest even, subnormals included (host side; |v| < 65520)
+__host__ inline uint32_t f16_bits(double v)
+{
+    const uint32_t sign = v < 0 ? 0x8000u : 0u;
+    const double a = v < 0 ? -v : v;
+    if (a == 0) return sign;
+    int e;
+    (void)frexp(a, &e);                       // a = f * 2^e, f in [0.5, 1)
+    int E = e - 1;                            // a = 1.m * 2^E
+    if (E < -14) {                            // subnormal: multiples of 2^-24
+        const uint32_t m = (uint32_t)nearbyint(ldexp(a, 24));
+        return sign | m;                      // m == 1024 is the smallest normal, same encoding
+    }
+    uint32_t m = (uint32_t)nearbyint(ldexp(a, 10 - E));   // in [1024, 2048]
+    if (m == 2048u) { m = 1024u; ++E; }
+    return sign | ((uint32_t)(E + 15) << 10) | (m - 1024u);
+}
+__host__ inline double f16_value(uint32_t b)
+{
+    const int e = (b >> 10) & 31, m = b & 1023;
+    const double x = e ? ldexp(1.0 + m / 1024.0, e - 15) : ldexp(m / 1024.0, -14);
+    return (b & 0x8000u) ? -x : x;
+}
+__host__ __device__ inline QuantSwar quant_swar(uint32_t error)   // the fp16 constants are filled on the host only
 {
     // (k, c, n) with ((x*k + c) >> n) == x / (2e+1) for all x in [e, 255+e] and x*k + c < 2^16
     uint32_t k = 0, c = 0, n = 0;
@@ -145,10 +221,73 @@ __host__ __device__ inline QuantSwar quant_swar(uint32_t error)
     q.scale = 2 * error + 1;
     q.rmask = (0xFu << n) * 0x00010001u;
     q.qmul = n ? (q.scale << (32 - n)) : 0u;
+    q.hK = q.hc1 = q.hS = q.hc2 = 0u;
+#ifndef __CUDA_ARCH__
+    if (error) {
+        // r = base + floor((d + e) / scale) / inv_ulp with base = 128 (ulp 1/8); e = 10 needs base = 64 (ulp 1/16)
+        // because 2^24 / (8 * 21) is not a finite fp16.  The offset 0.5 / scale centres the quotient between two
+        // multiples of 1 / scale, so the rounding of r never sees a tie: RN == floor.
+        const double scale = 2.0 * error + 1.0, base = error == 10 ? 64.0 : 128.0, inv_ulp = 1024.0 / base;
+        q.hK = f16_bits(16777216.0 / (inv_ulp * scale)) * 0x00010001u;
+        q.hc1 = f16_bits(base + (error / scale - 0.5 + 0.5 / scale) / inv_ulp) * 0x00010001u;
+        q.hS = f16_bits(ldexp(inv_ulp * scale, -24)) * 0x00010001u;
+        q.hc2 = f16_bits(-ldexp(1024.0 * scale, -24)) * 0x00010001u;
+    }
+#endif
     return q;
 }
 
+// the launchers evaluate the constants on the host, once per launch
+__host__ inline void fill_quant_args(PassArgs& a)
+{
+    const QuantSwar q = quant_swar(a.quant_error);
+    a.q_one = q.one; a.q_mul = q.mul; a.q_add = q.add; a.q_shift = q.shift; a.q_scale = q.scale; a.q_rmask = q.rmask; a.q_qmul = q.qmul;
+    a.q_hK = q.hK; a.q_hc1 = q.hc1; a.q_hS = q.hS; a.q_hc2 = q.hc2;
+}
+
 // src/encoder.rs:52-64 for two pixels.  Returns the symbols; `recon` = what the decoder rebuilds.
+// p, pk = 256 - p: clean lanes (pred_pk2).  Quantizer (src/quantizator.rs:50-60) on the FMA pipe: two HFMA2, see
+// QuantSwar; the lanes of q come out as plain integers.
+#ifndef HGI_VAR_INTQ
+#ifndef HGI_VAR_HMUL_MASKS
+#define HGI_VAR_HMUL_MASKS 2     // of the three fix-up masks per cell pair, how many are built on the FMA pipe (HMUL2) instead of the ALU pipe (VIMNMX)
+#endif
+template <bool IDENTITY, bool FMA_MASK = false>
+__device__ __forceinline__ uint32_t encode2(uint32_t a, uint32_t p, uint32_t pk, const QuantSwar& qc, uint32_t& recon)
+{
+    const uint32_t dd = fadd(a, pk, qc.one);          // per lane a + 256 - p: low byte = the residual, bit 8 = [a >= p]
+    if (IDENTITY) {
+        recon = a;                                    // p + (a - p) == a
+        return dd;                                    // low byte of each lane = the symbol; packed with pack_lo()
+    }
+    const uint32_t d = dd & M16;                      // :53 wrapping_sub
+    const uint32_t r = hfma2(d, qc.hK, qc.hc1);       // base + floor((d + e) / scale) * ulp
+    uint32_t q = hfma2(r, qc.hS, qc.hc2);             // :54 table[d]
+    const uint32_t ov = fadd(q, p, qc.one);           // bit 8 = overflow (p may carry the bias 512)  (:56)
+    // overflow_is_expected = [a < p] = !bit8(dd)  =>  mismatch iff bit8(ov) == bit8(dd)       (:57-58)
+    const uint32_t x = ~(ov ^ dd) & 0x01000100u;
+    uint32_t m;                                       // 0x00FF in every mismatching lane
+    if (FMA_MASK) m = hmul2(x, kH_255_256);           // 256 ulp * 255/256, exact
+    else asm("min.u16x2 %0, %1, %2;" : "=r"(m) : "r"(x), "r"(0x00FF00FFu));
+    q = (q & ~m) | (dd & m);                          // :59 (m only covers the low byte of a lane, so dd's flag bit drops out: one LOP3)
+    // :63 (p + q) mod 256.  p + d == a (mod 256) and, once the fix-up has run, a + (q - d) stays inside 0..255
+    // (that is exactly what the overflow test guards), so the lanes need neither a borrow nor a mask.
+    recon = a + q - d;
+    return q;
+}
+// the three new points of a cell pair (a1: even row, a2 / a3: odd row)
+template <int INTERP, bool IDENTITY>
+__device__ __forceinline__ void encode_cells(uint32_t A, uint32_t B, uint32_t C, uint32_t D, uint32_t a1, uint32_t a2, uint32_t a3,
+                                             const QuantSwar& qc, uint32_t (&q)[3], uint32_t (&r)[3])
+{
+    uint32_t p = 0u;
+    const uint32_t pk = pred_pk2<INTERP, !IDENTITY>(A, B, C, D, qc.one, p);
+    q[0] = encode2<IDENTITY, (HGI_VAR_HMUL_MASKS > 0)>(a1, p, pk, qc, r[0]);
+    q[1] = encode2<IDENTITY, (HGI_VAR_HMUL_MASKS > 1)>(a2, p, pk, qc, r[1]);
+    q[2] = encode2<IDENTITY, (HGI_VAR_HMUL_MASKS > 2)>(a3, p, pk, qc, r[2]);
+}
+#else
+// round-1 form (A/B variant): integer multiply-shift quantizer, predictor lanes with stray bits
 template <bool IDENTITY>
 __device__ __forceinline__ uint32_t encode2(uint32_t a, uint32_t p, uint32_t pk, const QuantSwar& qc, uint32_t& recon)
 {
@@ -173,6 +312,18 @@ __device__ __forceinline__ uint32_t encode2(uint32_t a, uint32_t p, uint32_t pk,
     recon = a + q - d;
     return q;
 }
+
+template <int INTERP, bool IDENTITY>
+__device__ __forceinline__ void encode_cells(uint32_t A, uint32_t B, uint32_t C, uint32_t D, uint32_t a1, uint32_t a2, uint32_t a3,
+                                             const QuantSwar& qc, uint32_t (&q)[3], uint32_t (&r)[3])
+{
+    const uint32_t p = pred2<INTERP, kDirtyEncodePred>(A, B, C, D, qc.one);
+    const uint32_t pk = bias_sub(p, qc.one);
+    q[0] = encode2<IDENTITY>(a1, p, pk, qc, r[0]);
+    q[1] = encode2<IDENTITY>(a2, p, pk, qc, r[1]);
+    q[2] = encode2<IDENTITY>(a3, p, pk, qc, r[2]);
+}
+#endif
 
 // src/decoder.rs:39 for two pixels; the low byte of each lane is the pixel (pack with pack_lo())
 __device__ __forceinline__ uint32_t decode2(uint32_t g, uint32_t p, uint32_t one) { return fadd(p, g, one); }
@@ -227,31 +378,28 @@ __device__ __forceinline__ void level_word(FastSmem& sm, int g, int cy, const Qu
     const uint32_t cwt = (uint32_t)*reinterpret_cast<const uint16_t*>(ct) | ((uint32_t)ct[2] << 16);
     const uint32_t cwb = (uint32_t)*reinterpret_cast<const uint16_t*>(ct + pc) | ((uint32_t)ct[pc + 2] << 16);
     const uint32_t A = lanes01(cwt), C = lanes12(cwt), B = lanes01(cwb), D = lanes12(cwb);
-    constexpr bool DIRTY = (MODE == kModeDecode) || kDirtyEncodePred;   // no consumer needs clean predictor lanes
-    const uint32_t p = pred2<INTERP, DIRTY>(A, B, C, D, qc.one);
     uint32_t* pev = reinterpret_cast<uint32_t*>(Ps + (2 * cy) * ps + 4 * g);
     uint32_t* pod = reinterpret_cast<uint32_t*>(Ps + (2 * cy + 1) * ps + 4 * g);
     const uint32_t ev = *pev, od = *pod;
     const uint32_t a1 = lanes_odd(ev), a2 = lanes_even(od), a3 = lanes_odd(od);   // clean: p may be dirty, the sums must stay < 2^16
-    uint32_t r1, r2, r3;
+    uint32_t r[3];
     if (MODE == kModeEncode) {
-        const uint32_t pk = bias_sub(p, qc.one);
-        const uint32_t q1 = encode2<IDENTITY>(a1, p, pk, qc, r1);
-        const uint32_t q2 = encode2<IDENTITY>(a2, p, pk, qc, r2);
-        const uint32_t q3 = encode2<IDENTITY>(a3, p, pk, qc, r3);
+        uint32_t q[3];
+        encode_cells<INTERP, IDENTITY>(A, B, C, D, a1, a2, a3, qc, q, r);
         uint8_t* Qs = sm.Q + plane_off(S);
         const uint8_t* Qc = sm.Q + plane_off(2 * S);
         const uint32_t qcw = (uint32_t)*reinterpret_cast<const uint16_t*>(Qc + cy * pc + 2 * g);
-        *reinterpret_cast<uint32_t*>(Qs + (2 * cy) * ps + 4 * g) = pack_even_row(qcw, q1, false);
-        *reinterpret_cast<uint32_t*>(Qs + (2 * cy + 1) * ps + 4 * g) = pack_sym<IDENTITY>(q2, q3);
+        *reinterpret_cast<uint32_t*>(Qs + (2 * cy) * ps + 4 * g) = pack_even_row(qcw, q[0], false);
+        *reinterpret_cast<uint32_t*>(Qs + (2 * cy + 1) * ps + 4 * g) = pack_sym<IDENTITY>(q[1], q[2]);
     } else {
-        r1 = decode2(a1, p, qc.one);
-        r2 = decode2(a2, p, qc.one);
-        r3 = decode2(a3, p, qc.one);
+        const uint32_t p = pred2<INTERP, true>(A, B, C, D, qc.one);   // no consumer needs clean predictor lanes
+        r[0] = decode2(a1, p, qc.one);
+        r[1] = decode2(a2, p, qc.one);
+        r[2] = decode2(a3, p, qc.one);
     }
     uint32_t wev, wod;
-    if (MODE == kModeDecode) { wev = pack_lo(A, r1); wod = pack_lo(r2, r3); }   // r = p + g with carry bits
-    else { wev = interleave(A, r1); wod = interleave(r2, r3); }               // encode: recon lanes are clean
+    if (MODE == kModeDecode) { wev = pack_lo(A, r[0]); wod = pack_lo(r[1], r[2]); }   // r = p + g with carry bits
+    else { wev = interleave(A, r[0]); wod = interleave(r[1], r[2]); }               // encode: recon lanes are clean
     if (edge) {   // out-of-image reconstruction must read as 0 (src/interpolator.rs:75-82)
         wev &= valid_mask(4 * g, 2 * cy, xin_s, yin_s);
         wod &= valid_mask(4 * g, 2 * cy + 1, xin_s, yin_s);
@@ -271,7 +419,6 @@ __device__ __forceinline__ void level2_owner(FastSmem& sm, const uint4& r0, cons
                                              uint32_t (&p2e)[2], uint32_t (&p2o)[2], uint32_t (&q2e)[2], uint32_t (&q2o)[2])
 {
     constexpr int ps = plane_pitch(2), pc = plane_pitch(4);
-    constexpr bool DIRTY = (MODE == kModeDecode) || kDirtyEncodePred;
     const int xin_s = (int)(((uint32_t)xin + 1) / 2u), yin_s = (int)(((uint32_t)yin + 1) / 2u);
     const uint8_t* ct = sm.P + plane_off(4) + ry * pc + 4 * sx;
     const uint32_t ctw = *reinterpret_cast<const uint32_t*>(ct), cte = ct[4];
@@ -284,24 +431,22 @@ __device__ __forceinline__ void level2_owner(FastSmem& sm, const uint4& r0, cons
     for (int k = 0; k < 2; ++k) {
         const uint32_t A = k ? lanes23(ctw) : lanes01(ctw), C = k ? prmt(ctw, cte, 0x5453u) : lanes12(ctw);
         const uint32_t B = k ? lanes23(cbw) : lanes01(cbw), D = k ? prmt(cbw, cbe, 0x5453u) : lanes12(cbw);
-        const uint32_t p = pred2<INTERP, DIRTY>(A, B, C, D, qc.one);
         const uint32_t a1 = lanes_odd(evw[k]), a2 = lanes_even(odw[k]), a3 = lanes_odd(odw[k]);
-        uint32_t r1v, r2v, r3v;
+        uint32_t r[3];
         if (MODE == kModeEncode) {
-            const uint32_t pk = bias_sub(p, qc.one);
-            const uint32_t q1 = encode2<IDENTITY>(a1, p, pk, qc, r1v);
-            const uint32_t q2 = encode2<IDENTITY>(a2, p, pk, qc, r2v);
-            const uint32_t q3 = encode2<IDENTITY>(a3, p, pk, qc, r3v);
-            q2e[k] = pack_even_row(qcw, q1, k != 0);
-            q2o[k] = pack_sym<IDENTITY>(q2, q3);
+            uint32_t q[3];
+            encode_cells<INTERP, IDENTITY>(A, B, C, D, a1, a2, a3, qc, q, r);
+            q2e[k] = pack_even_row(qcw, q[0], k != 0);
+            q2o[k] = pack_sym<IDENTITY>(q[1], q[2]);
         } else {
-            r1v = decode2(a1, p, qc.one);
-            r2v = decode2(a2, p, qc.one);
-            r3v = decode2(a3, p, qc.one);
+            const uint32_t p = pred2<INTERP, true>(A, B, C, D, qc.one);
+            r[0] = decode2(a1, p, qc.one);
+            r[1] = decode2(a2, p, qc.one);
+            r[2] = decode2(a3, p, qc.one);
         }
         uint32_t wev, wod;
-        if (MODE == kModeDecode) { wev = pack_lo(A, r1v); wod = pack_lo(r2v, r3v); }
-        else { wev = interleave(A, r1v); wod = interleave(r2v, r3v); }
+        if (MODE == kModeDecode) { wev = pack_lo(A, r[0]); wod = pack_lo(r[1], r[2]); }
+        else { wev = interleave(A, r[0]); wod = interleave(r[1], r[2]); }
         if (edge) {   // out-of-image reconstruction must read as 0 (src/interpolator.rs:75-82)
             wev &= valid_mask(8 * sx + 4 * k, 2 * ry, xin_s, yin_s);
             wod &= valid_mask(8 * sx + 4 * k, 2 * ry + 1, xin_s, yin_s);

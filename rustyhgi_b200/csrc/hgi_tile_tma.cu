@@ -92,12 +92,11 @@ hgi_tile_tma_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
     FastSmem& sm = *reinterpret_cast<FastSmem*>(dyn_smem + 2 * RAW_BYTES);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(dyn_smem + 2 * RAW_BYTES + sizeof(FastSmem));
     constexpr int F = 1 << NLEV;
-    constexpr bool DIRTY = (MODE == kModeDecode);   // decode only consumes the low byte of each predictor lane
 
     const int tid = threadIdx.x;
     const int sx = tid & 7, ry = tid >> 3;          // 8 column strips x TH/2 row pairs
     const bool top = (p.c_recon == nullptr);
-    const QuantSwar qc = quant_swar(p.quant_error);
+    const QuantSwar qc = {p.q_one, p.q_mul, p.q_add, p.q_shift, p.q_scale, p.q_rmask, p.q_qmul, p.q_hK, p.q_hc1, p.q_hS, p.q_hc2};   // filled by the launcher
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -212,23 +211,19 @@ hgi_tile_tma_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
             if (MODE == kModeEncode) qcw = *reinterpret_cast<const uint2*>(sm.Q + plane_off(2) + ry * plane_pitch(2) + 8 * sx);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t pr = pred2<INTERP, DIRTY>(A[k], B[k], C[k], D[k], qc.one);
                 const uint32_t a1 = lanes_odd(evw[k]), a2 = lanes_even(odw[k]), a3 = lanes_odd(odw[k]);
                 if (MODE == kModeEncode) {
-                    uint32_t r1, r2, r3;
-                    const uint32_t pk = 0x01000100u - pr;
-                    const uint32_t q1 = encode2<IDENTITY>(a1, pr, pk, qc, r1);
-                    const uint32_t q2 = encode2<IDENTITY>(a2, pr, pk, qc, r2);
-                    const uint32_t q3 = encode2<IDENTITY>(a3, pr, pk, qc, r3);
+                    uint32_t q[3], r[3];
+                    encode_cells<INTERP, IDENTITY>(A[k], B[k], C[k], D[k], a1, a2, a3, qc, q, r);
                     const uint32_t qw = (k < 2) ? qcw.x : qcw.y;
-                    const uint32_t QA = (k & 1) ? lanes23(qw) : lanes01(qw);
-                    out_ev[k] = pack_sym<IDENTITY>(QA, q1);
-                    out_od[k] = pack_sym<IDENTITY>(q2, q3);
+                    out_ev[k] = pack_even_row(qw, q[0], (k & 1) != 0);
+                    out_od[k] = pack_sym<IDENTITY>(q[1], q[2]);
                     if (EXTRA) {
-                        rec_ev[k] = interleave(A[k], r1);
-                        rec_od[k] = interleave(r2, r3);
+                        rec_ev[k] = interleave(A[k], r[0]);
+                        rec_od[k] = interleave(r[1], r[2]);
                     }
                 } else {
+                    const uint32_t pr = pred2<INTERP, true>(A[k], B[k], C[k], D[k], qc.one);
                     out_ev[k] = pack_lo(A[k], decode2(a1, pr, qc.one));
                     out_od[k] = pack_lo(decode2(a2, pr, qc.one), decode2(a3, pr, qc.one));
                 }
@@ -365,8 +360,10 @@ cudaError_t launch_tma_t(const PassArgs& a, cudaStream_t stream, bool* used)
 
 // Returns cudaSuccess with *used == false when the TMA path cannot serve this launch (no driver entry point,
 // tensor-map limits); the caller then uses the register-prefetch kernel.
-cudaError_t launch_tile_pass_tma(int mode, int interp, const PassArgs& a, cudaStream_t stream, bool* used)
+cudaError_t launch_tile_pass_tma(int mode, int interp, const PassArgs& args, cudaStream_t stream, bool* used)
 {
+    PassArgs a = args;
+    fill_quant_args(a);
     if (mode == kModeEncode)
         return interp == kInterpLeftTop ? launch_tma_t<kModeEncode, kInterpLeftTop>(a, stream, used)
                                         : launch_tma_t<kModeEncode, kInterpCrossed>(a, stream, used);

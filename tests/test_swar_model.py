@@ -157,3 +157,120 @@ def test_lanewise_bias_tolerates_dirty_predictor_lanes():
         assert ((dd >> 8) & 1, (dd >> 24) & 1) == (int(a0 >= p0), int(a1 >= p1))
         ov = ((q0 | (q1 << 16)) + p) & U32
         assert ((ov >> 8) & 1, (ov >> 24) & 1) == (int(q0 + p0 > 255), int(q1 + p1 > 255))
+
+
+# ---- fp16x2 arithmetic on integer lanes (hgi_tile_swar.cuh: hfma2 / pred_pk2 / encode2) -------------------------
+# A lane holding an integer n < 2048 is the fp16 number n * 2^-24; HFMA2 is modelled as an exact product and sum in
+# float64 (22-bit product, < 53 bits after the add) followed by ONE rounding to fp16 (numpy: nearest even, subnormals kept).
+def _h2f(bits):
+    return float(np.array([bits], dtype=np.uint16).view(np.float16)[0])
+
+
+def _f2h(v):
+    with np.errstate(over="raise"):
+        return int(np.array([v], dtype=np.float64).astype(np.float16).view(np.uint16)[0])
+
+
+def hfma_lane(a, b, c):
+    return _f2h(_h2f(a) * _h2f(b) + _h2f(c))
+
+
+def hfma2(a, b, c):
+    return hfma_lane(a & 0xFFFF, b & 0xFFFF, c & 0xFFFF) | (hfma_lane(a >> 16, b >> 16, c >> 16) << 16)
+
+
+def f16_quant_constants(error):
+    """quant_swar(): hK, hc1, hS, hc2 (one lane)."""
+    scale = 2.0 * error + 1.0
+    base = 64.0 if error == 10 else 128.0
+    inv_ulp = 1024.0 / base
+    return (_f2h(16777216.0 / (inv_ulp * scale)), _f2h(base + (error / scale - 0.5 + 0.5 / scale) / inv_ulp),
+            _f2h(inv_ulp * scale * 2.0 ** -24), _f2h(-1024.0 * scale * 2.0 ** -24))
+
+
+H_EIGHTH, H_NEG_EIGHTH, H_511ULP, H_257ULP, H_255_256 = 0x3000, 0xB000, 0x01FF, 0x0101, 0x3BF8
+
+
+def fp16_pred_pk(A, B, C, D):
+    """pred_pk2<Crossed>: (p + 512 lanes, pk lanes) from clean corner lanes."""
+    x1 = (A ^ B) & 0x00010001
+    w = x1 & (C ^ D) & (A ^ C)
+    yb = (2 * (A + B + C) + 2 * D + 0x00070007 + 4 * w) & U32
+    assert (yb & 0xFFFF) < 2048 and (yb >> 16) < 2048          # inside the range where lane bits == value * 2^24
+    rep = lambda h: h | (h << 16)
+    return hfma2(yb, rep(H_EIGHTH), rep(H_511ULP)), hfma2(yb, rep(H_NEG_EIGHTH), rep(H_257ULP))
+
+
+def test_fp16_constants_are_what_the_header_says():
+    assert _h2f(H_EIGHTH) == 0.125 and _h2f(H_NEG_EIGHTH) == -0.125 and _h2f(H_511ULP) == 511 * 2.0 ** -24
+    assert _h2f(H_257ULP) == 257 * 2.0 ** -24 and _h2f(H_255_256) == 255 / 256
+    for n in list(range(0, 2048, 7)) + [1023, 1024, 1025, 2047]:
+        assert _h2f(n) == n * 2.0 ** -24                        # subnormals and the first normal binade share the ulp
+
+
+def test_fp16_predictor_matches_reference():
+    vals = [0, 1, 2, 3, 4, 5, 126, 127, 128, 129, 252, 253, 254, 255]
+    for A, B, C, D in itertools.product(vals, repeat=4):
+        A2, B2, C2, D2 = 255 - A, B ^ 1, (C + 77) & 255, D       # a different cell in the other lane
+        p, pk = fp16_pred_pk(A | (A2 << 16), B | (B2 << 16), C | (C2 << 16), D | (D2 << 16))
+        r0, r1 = ref_pred(A, B, C, D), ref_pred(A2, B2, C2, D2)
+        assert (p & 0xFFFF, p >> 16) == (r0 + 512, r1 + 512) and (pk & 0xFFFF, pk >> 16) == (256 - r0, 256 - r1)
+    rng = np.random.default_rng(11)
+    for v in rng.integers(0, 256, (20000, 8)):
+        A, B, C, D, A2, B2, C2, D2 = (int(x) for x in v)
+        p, pk = fp16_pred_pk(A | (A2 << 16), B | (B2 << 16), C | (C2 << 16), D | (D2 << 16))
+        assert (p & 0xFFFF, p >> 16) == (ref_pred(A, B, C, D) + 512, ref_pred(A2, B2, C2, D2) + 512)
+        assert pk == (0x03000300 - p) & U32
+
+
+def test_fp16_quantizer_is_exact_for_every_residual():
+    for error in (10, 20, 30):
+        hK, hc1, hS, hc2 = f16_quant_constants(error)
+        scale = 2 * error + 1
+        for d in range(256):
+            r = hfma_lane(d, hK, hc1)
+            assert hfma_lane(r, hS, hc2) == ((d + error) // scale) * scale, (error, d)
+
+
+def fp16_encode2(a, p, pk, error, fma_mask):
+    """encode2<false, FMA_MASK>: returns (q lanes, recon lanes)."""
+    hK, hc1, hS, hc2 = (h | (h << 16) for h in f16_quant_constants(error))
+    dd = (a + pk) & U32
+    d = dd & M16
+    q = hfma2(hfma2(d, hK, hc1), hS, hc2)
+    ov = (q + p) & U32
+    x = (~(ov ^ dd)) & 0x01000100
+    if fma_mask:                                               # 0x0100 * 255/256 == 0x00FF, exact
+        m = hfma2(x, H_255_256 | (H_255_256 << 16), 0)
+    else:
+        m = min(x & 0xFFFF, 0xFF) | (min(x >> 16, 0xFF) << 16)
+    q = (q & ~m & U32) | (dd & m)
+    return q, (a + q - d) & U32
+
+
+def test_fp16_encode_point_exhaustive():
+    """All (a, p) pairs, every Linear level, both mask variants: symbol and reconstruction."""
+    cache = {}
+    for level, error in ((1, 10), (2, 20), (3, 30)):
+        table, _ = oc.quant_table(oc.QUANT_LINEAR, level)
+        hK, hc1, hS, hc2 = f16_quant_constants(error)
+        qt = [hfma_lane(hfma_lane(d, hK, hc1), hS, hc2) for d in range(256)]     # per-lane quantizer, memoised
+        for p0 in range(256):
+            for a0 in range(256):
+                dd = a0 + 256 - p0
+                d = dd & 255
+                q = qt[d]
+                ov = q + p0 + 512                                # pred_pk2 hands over p + 512
+                x = (~(ov ^ dd)) & 0x0100
+                for m in (min(x, 0xFF), hfma_lane(x, H_255_256, 0)):
+                    qq = (q & ~m) | (dd & m & 0xFFFF)
+                    assert (qq, (a0 + qq - d) & 0xFFFF) == ref_encode(a0, p0, table), (level, a0, p0)
+    # the two-lane form on a sample (lane independence)
+    rng = np.random.default_rng(5)
+    table, _ = oc.quant_table(oc.QUANT_LINEAR, 2)
+    for v in rng.integers(0, 256, (3000, 4)):
+        a0, a1, p0, p1 = (int(x) for x in v)
+        p = p0 | (p1 << 16)
+        for fm in (False, True):
+            q, r = fp16_encode2(a0 | (a1 << 16), p + 0x02000200, (0x01000100 - p) & U32, 20, fm)
+            assert (q & 0xFFFF, r & 0xFFFF) == ref_encode(a0, p0, table) and (q >> 16, r >> 16) == ref_encode(a1, p1, table)
