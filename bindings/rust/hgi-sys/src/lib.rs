@@ -69,6 +69,12 @@ extern "C" {
                           d_hist_out: *mut u32, stream: *mut c_void) -> c_int;
     pub fn hgi_decode_dev(ctx: *mut hgi_ctx_t, d_grids: *const u8, n_images: u32, width: u32, height: u32,
                           params: *const hgi_params_t, d_images_out: *mut u8, stream: *mut c_void) -> c_int;
+    pub fn hgi_encode_dev_pitched(ctx: *mut hgi_ctx_t, d_images: *const u8, n_images: u32, width: u32, height: u32,
+                                  pitch: u32, params: *const hgi_params_t, d_grids_out: *mut u8, d_recon_out: *mut u8,
+                                  d_hist_out: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn hgi_decode_dev_pitched(ctx: *mut hgi_ctx_t, d_grids: *const u8, n_images: u32, width: u32, height: u32,
+                                  pitch: u32, params: *const hgi_params_t, d_images_out: *mut u8,
+                                  stream: *mut c_void) -> c_int;
     pub fn hgi_rgb_to_luma_dev(ctx: *mut hgi_ctx_t, d_rgb: *const u8, n_pixels: usize, d_luma_out: *mut u8,
                                stream: *mut c_void) -> c_int;
     pub fn hgi_histogram_dev(ctx: *mut hgi_ctx_t, d_grid: *const u8, n_per_image: usize, n_images: u32,

@@ -18,6 +18,8 @@
  *    void*; NULL = the context's own stream) without synchronising.
  *  - A context is bound to one CUDA device; calls on one context are stream-ordered and must not
  *    be issued concurrently from several host threads.  Distinct contexts are independent.
+ *    `*_dev` calls on different streams of one context may overlap on the device: each stream
+ *    gets its own scratch planes (the 32 most recently used streams are kept).
  *  - There is no CPU fallback: if no CUDA device is usable, hgi_ctx_create fails.
  */
 #ifndef HGI_H_
@@ -77,6 +79,8 @@ typedef enum {
 } hgi_path_t;
 
 #define HGI_MAX_LEVELS 31u
+/* Rows (width, pitch) must be shorter than this many bytes: the kernels keep tile-relative offsets in 32 bits. */
+#define HGI_MAX_ROW_BYTES (1u << 26)
 
 /* Encoder/decoder options: `Encoder::new(interpolator, quantizator, scale_level)`
    (src/encoder.rs:18-24) and `Decoder::new(interpolator)` + `levels` (src/decoder.rs:14-18). */
@@ -158,6 +162,18 @@ int hgi_rgb_to_luma_dev(hgi_ctx_t *ctx, const uint8_t *d_rgb, size_t n_pixels, u
 int hgi_histogram_dev(hgi_ctx_t *ctx, const uint8_t *d_grid, size_t n_per_image,
                       uint32_t n_images, uint32_t *d_hist_out /* [n_images][256], overwritten */,
                       void *stream);
+/* The same for planes whose rows are `pitch` bytes apart (pitch >= width; image k starts at k * pitch * height in
+   every plane argument, all planes share the pitch).  A pitch that is a multiple of 16 with 16-byte-aligned bases
+   puts any width on the 128-bit path: pad the rows of odd-width planes instead of packing them.  Input bytes in
+   the padding are ignored; output bytes in the padding are unspecified.  pitch == width is hgi_encode_dev /
+   hgi_decode_dev.  Not available on HGI_PATH_PER_LEVEL (-> HGI_ERR_UNSUPPORTED). */
+int hgi_encode_dev_pitched(hgi_ctx_t *ctx, const uint8_t *d_images, uint32_t n_images, uint32_t width,
+                           uint32_t height, uint32_t pitch, const hgi_params_t *params,
+                           uint8_t *d_grids_out, uint8_t *d_recon_out /* nullable */,
+                           uint32_t *d_hist_out /* nullable */, void *stream);
+int hgi_decode_dev_pitched(hgi_ctx_t *ctx, const uint8_t *d_grids, uint32_t n_images, uint32_t width,
+                           uint32_t height, uint32_t pitch, const hgi_params_t *params,
+                           uint8_t *d_images_out, void *stream);
 /* d_out[0] = sum of squares, d_out[1] = max abs (both u64, overwritten). */
 int hgi_error_metrics_dev(hgi_ctx_t *ctx, const uint8_t *d_before, const uint8_t *d_after,
                           size_t n, uint64_t *d_out, void *stream);

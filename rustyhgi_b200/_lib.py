@@ -55,6 +55,8 @@ PROTOTYPES = {
     "hgi_rgb_to_luma_dev": (_int, [_vp, _vp, _sz, _vp, _vp]),
     "hgi_encode_dev": (_int, [_vp, _vp, _u32, _u32, _u32, _pp, _vp, _vp, _vp, _vp]),
     "hgi_decode_dev": (_int, [_vp, _vp, _u32, _u32, _u32, _pp, _vp, _vp]),
+    "hgi_encode_dev_pitched": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _pp, _vp, _vp, _vp, _vp]),
+    "hgi_decode_dev_pitched": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _pp, _vp, _vp]),
     "hgi_histogram_dev": (_int, [_vp, _vp, _sz, _u32, _vp, _vp]),
     "hgi_error_metrics_dev": (_int, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "hgi_archive_bound": (_sz, [_sz]),

@@ -163,6 +163,32 @@ def _stream_handle(stream, device):
     return h if h else 1
 
 
+def _dev_planes(t, what):
+    """(tensor as (n, h, w), n, h, w, pitch) for a CUDA uint8 tensor (n, h, w) or (h, w) whose rows are contiguous:
+    either packed, or a `[..., :w]` view of a buffer with padded rows (pitch = stride of the row dimension)."""
+    import torch
+    v = t if t.dim() == 3 else t.unsqueeze(0)
+    if not (v.is_cuda and v.dtype == torch.uint8 and v.dim() == 3):
+        raise TypeError(f"{what} must be a CUDA uint8 tensor (n, h, w) or (h, w)")
+    n, h, w = v.shape
+    if n * h * w == 0 or v.is_contiguous():
+        return v, n, h, w, w
+    pitch = v.stride(1)
+    if v.stride(2) != 1 or pitch < w or (n > 1 and v.stride(0) != pitch * h):
+        raise ValueError(f"{what}: rows must be contiguous and images pitch * height bytes apart")
+    return v, n, h, w, pitch
+
+
+def _ctx_for(explicit, tensor):
+    """The context of a device call: the explicit one (which must live on the tensor's device) or the per-device default."""
+    dev = tensor.device.index if tensor.device.index is not None else 0
+    if explicit is None:
+        return Context.default(dev)
+    if explicit.device != dev:
+        raise ValueError(f"context is bound to cuda:{explicit.device} but the tensor lives on cuda:{dev}")
+    return explicit
+
+
 class Grid:
     """src/grid.rs:1-5: `buffer` (row-major u8, stride = width) + `width`."""
 
@@ -227,21 +253,23 @@ class Encoder:
         return (grids, hist) if want_hist else grids
 
     def encode_device(self, images, grids_out=None, recon_out=None, hist_out=None, stream=None):
-        """Device-resident batch: `images` is a CUDA uint8 torch tensor (n, h, w) or (h, w)."""
+        """Device-resident batch: `images` is a CUDA uint8 torch tensor (n, h, w) or (h, w), packed or with padded
+        rows (see _dev_planes); the outputs must have the same layout."""
         import torch
-        t = images if images.dim() == 3 else images.unsqueeze(0)
-        assert t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous()
-        n, h, w = t.shape
+        t, n, h, w, pitch = _dev_planes(images, "images")
+        ctx = _ctx_for(self._ctx, t)
         if grids_out is None:
-            grids_out = torch.empty_like(t)
-        assert grids_out.is_contiguous() and grids_out.numel() == t.numel()
+            grids_out = torch.empty_strided(t.shape, t.stride(), dtype=torch.uint8, device=t.device)
+        for o, what in ((grids_out, "grids_out"), (recon_out, "recon_out")):
+            if o is not None and _dev_planes(o, what)[1:] != (n, h, w, pitch):
+                raise ValueError(f"{what} must have the shape and row pitch of images")
         st = _stream_handle(stream, t.device)
         p = self._p()
-        rc = _lib.lib().hgi_encode_dev(self.ctx._h, t.data_ptr(), n, w, h, ctypes.byref(p), grids_out.data_ptr(),
-                                       recon_out.data_ptr() if recon_out is not None else None,
-                                       hist_out.data_ptr() if hist_out is not None else None, st)
-        self.ctx.check(rc, "hgi_encode_dev")
-        return grids_out.view(images.shape)
+        rc = _lib.lib().hgi_encode_dev_pitched(ctx._h, t.data_ptr(), n, w, h, pitch, ctypes.byref(p), grids_out.data_ptr(),
+                                               recon_out.data_ptr() if recon_out is not None else None,
+                                               hist_out.data_ptr() if hist_out is not None else None, st)
+        ctx.check(rc, "hgi_encode_dev_pitched")
+        return grids_out if grids_out.dim() == images.dim() else grids_out[0]
 
 
 class Decoder:
@@ -279,16 +307,17 @@ class Decoder:
 
     def decode_device(self, levels, grids, images_out=None, stream=None):
         import torch
-        t = grids if grids.dim() == 3 else grids.unsqueeze(0)
-        assert t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous()
-        n, h, w = t.shape
+        t, n, h, w, pitch = _dev_planes(grids, "grids")
+        ctx = _ctx_for(self._ctx, t)
         if images_out is None:
-            images_out = torch.empty_like(t)
+            images_out = torch.empty_strided(t.shape, t.stride(), dtype=torch.uint8, device=t.device)
+        if _dev_planes(images_out, "images_out")[1:] != (n, h, w, pitch):
+            raise ValueError("images_out must have the shape and row pitch of grids")
         st = _stream_handle(stream, t.device)
         p = _params(levels, self._interp)
-        rc = _lib.lib().hgi_decode_dev(self.ctx._h, t.data_ptr(), n, w, h, ctypes.byref(p), images_out.data_ptr(), st)
-        self.ctx.check(rc, "hgi_decode_dev")
-        return images_out.view(grids.shape)
+        rc = _lib.lib().hgi_decode_dev_pitched(ctx._h, t.data_ptr(), n, w, h, pitch, ctypes.byref(p), images_out.data_ptr(), st)
+        ctx.check(rc, "hgi_decode_dev_pitched")
+        return images_out if images_out.dim() == grids.dim() else images_out[0]
 
 
 def histogram(grid, ctx=None):

@@ -13,7 +13,17 @@
 
 namespace {
 
-constexpr int kSlots = 3;  // host-API pipeline depth (H2D / kernels / D2H overlap)
+constexpr int kSlots = 4;  // host-API pipeline: at most this many chunks in flight (H2D / kernels / D2H overlap)
+// Slots actually used; HGI_B200_SLOTS overrides (tuning hook, 1..kSlots).
+int slot_count()
+{
+    static const int v = [] {
+        const char* e = std::getenv("HGI_B200_SLOTS");
+        const long n = e ? std::atol(e) : 0;
+        return (int)(n >= 1 && n <= kSlots ? n : 3);
+    }();
+    return v;
+}
 // Bytes per pipeline chunk of the host-pointer entry points; HGI_B200_CHUNK_MB overrides (tuning hook).
 size_t chunk_bytes()
 {
@@ -30,12 +40,29 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+// Device scratch of ONE stream's launch chain.  Chains on different streams may run at the same time (the slots of
+// the host API, caller streams of the device API), so every stream owns its set: sharing one set let a chunk's fine
+// pass read the next chunk's coarse planes.
+struct Scratch {
+    DevBuf compact[4];   // ping-pong {recon, q} compact planes of the coarse passes
+    DevBuf dec_in;       // decimated source of a coarse pass
+    DevBuf level_recon;  // per-level path: reconstruction planes when the caller gives none
+};
+
 struct Slot {
     cudaStream_t stream = nullptr;
     DevBuf in, out, aux;
     uint32_t* hist = nullptr;
     size_t hist_cap = 0;
+    Scratch scratch;
 };
+
+struct StreamScratch {
+    cudaStream_t stream;
+    Scratch scratch;
+};
+
+constexpr size_t kMaxCallerStreams = 32;   // scratch sets kept for device-API caller streams; the oldest is recycled
 
 }  // namespace
 
@@ -45,8 +72,7 @@ struct hgi_ctx {
     cudaStream_t stream = nullptr;
     cudaError_t last_err = cudaSuccess;
     uint64_t launches = 0;
-    DevBuf compact[4];   // ping-pong {recon, q} compact planes of the coarse passes
-    DevBuf level_recon;  // per-level path: reconstruction planes when the caller gives none
+    std::vector<StreamScratch*> caller_scratch;   // device API: one scratch set per caller stream
     Slot slots[kSlots];
     unsigned long long* d_metrics = nullptr;
 };
@@ -100,6 +126,42 @@ int reserve(hgi_ctx* ctx, DevBuf& b, size_t bytes)
     return HGI_OK;
 }
 
+void free_scratch(Scratch& sc)
+{
+    for (auto& b : sc.compact) if (b.p) { cudaFree(b.p); b = DevBuf{}; }
+    if (sc.dec_in.p) { cudaFree(sc.dec_in.p); sc.dec_in = DevBuf{}; }
+    if (sc.level_recon.p) { cudaFree(sc.level_recon.p); sc.level_recon = DevBuf{}; }
+}
+
+// Scratch set of a device-API caller stream (created on first use).
+Scratch* scratch_for(hgi_ctx* ctx, cudaStream_t st)
+{
+    for (size_t i = 0; i < ctx->caller_scratch.size(); ++i)
+        if (ctx->caller_scratch[i]->stream == st) {
+            if (i + 1 != ctx->caller_scratch.size()) {   // keep most-recently-used order
+                StreamScratch* hit = ctx->caller_scratch[i];
+                ctx->caller_scratch.erase(ctx->caller_scratch.begin() + (long)i);
+                ctx->caller_scratch.push_back(hit);
+            }
+            return &ctx->caller_scratch.back()->scratch;
+        }
+    if (ctx->caller_scratch.size() >= kMaxCallerStreams) {
+        // recycle the least recently used set: nothing of it may still be in flight (the stream may be gone: ignore errors)
+        StreamScratch* old = ctx->caller_scratch.front();
+        ctx->caller_scratch.erase(ctx->caller_scratch.begin());
+        (void)cudaDeviceSynchronize();
+        (void)cudaGetLastError();
+        old->stream = st;
+        ctx->caller_scratch.push_back(old);
+        return &old->scratch;
+    }
+    StreamScratch* ss = new (std::nothrow) StreamScratch();
+    if (!ss) return nullptr;
+    ss->stream = st;
+    ctx->caller_scratch.push_back(ss);
+    return &ss->scratch;
+}
+
 int check_params(const hgi_params_t* p, bool encode)
 {
     if (!p) return HGI_ERR_INVALID_ARG;
@@ -149,42 +211,50 @@ inline uint32_t ceil_shift(uint32_t v, uint32_t sh)
 
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
-// mode: hgi::kModeEncode / kModeDecode.  All pointers are device pointers.
-int run_tile_path(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images, uint32_t w, uint32_t h,
-                  uint32_t levels, const hgi_params_t* prm, uint8_t* grid_out, uint8_t* recon_out, cudaStream_t st)
+inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
+
+// mode: hgi::kModeEncode / kModeDecode.  All pointers are device pointers; planes have rows of `pitch` bytes.
+int run_tile_path(hgi_ctx* ctx, Scratch& sc, int mode, const uint8_t* src, uint32_t n_images, uint32_t w, uint32_t h,
+                  uint32_t pitch, uint32_t levels, const hgi_params_t* prm, uint8_t* grid_out, uint8_t* recon_out,
+                  cudaStream_t st)
 {
     const std::vector<Pass> passes = plan_passes(levels);
     const uint32_t qerr = (mode == hgi::kModeEncode) ? hgi::level_error(prm->quant_kind, prm->quant_level) : 0u;
-    // compact planes: pass i (D>1) writes set (i&1), the next pass reads it
+    // compact planes (rows padded to 16 bytes): pass i (D>1) writes set (i&1), the next pass reads it
     size_t max_compact = 0;
     for (const Pass& ps : passes)
         if (ps.d_log2 > 0) {
-            const size_t sz = (size_t)n_images * ceil_shift(w, ps.d_log2) * ceil_shift(h, ps.d_log2);
+            const size_t sz = (size_t)n_images * align16(ceil_shift(w, ps.d_log2)) * ceil_shift(h, ps.d_log2);
             if (sz > max_compact) max_compact = sz;
         }
     if (max_compact) {
         const int nbuf = passes.size() > 2 ? 4 : 2;
         for (int i = 0; i < nbuf; ++i) {
             if (mode == hgi::kModeDecode && (i & 1)) continue;  // decode carries no symbols
-            int rc = reserve(ctx, ctx->compact[i], max_compact);
+            int rc = reserve(ctx, sc.compact[i], max_compact);
             if (rc) return rc;
         }
+        int rc = reserve(ctx, sc.dec_in, max_compact);
+        if (rc) return rc;
     }
     const uint8_t* c_recon = nullptr;
     const uint8_t* c_q = nullptr;
-    uint32_t cw = 0, ch = 0;
+    uint32_t cw = 0, ch = 0, cpitch = 0;
     for (size_t i = 0; i < passes.size(); ++i) {
         const Pass& ps = passes[i];
         hgi::PassArgs a{};
         a.src = src;
         a.w = w;
         a.h = h;
+        a.pitch = pitch;
         a.d_log2 = ps.d_log2;
         a.nlev = ps.nlev;
         a.wD = ceil_shift(w, ps.d_log2);
         a.hD = ceil_shift(h, ps.d_log2);
+        a.dpitch = align16(a.wD);
         a.cw = cw;
         a.ch = ch;
+        a.cpitch = cpitch;
         a.c_recon = c_recon;
         a.c_q = c_q;
         a.tiles_x = (a.wD + hgi::kTileW - 1) / hgi::kTileW;
@@ -194,12 +264,13 @@ int run_tile_path(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images,
         if (ps.d_log2 == 0) {
             a.grid_out = grid_out;
             a.recon_out = recon_out;
-            a.vec_ok = (w % 16 == 0) && aligned16(src) && (grid_out == nullptr || aligned16(grid_out)) &&
+            a.vec_ok = (pitch % 16 == 0) && aligned16(src) && (grid_out == nullptr || aligned16(grid_out)) &&
                        (recon_out == nullptr || aligned16(recon_out));
         } else {
             const int set = (int)(i & 1) * 2;
-            a.s_recon = ctx->compact[set].p;
-            a.s_q = ctx->compact[set + 1].p;
+            a.s_recon = sc.compact[set].p;
+            a.s_q = sc.compact[set + 1].p;
+            a.dec_in = sc.dec_in.p;
         }
         const int variant = ctx->path == HGI_PATH_TILE_GENERIC ? hgi::kTileGeneric
                             : (ctx->path == HGI_PATH_TILE_TMA ? hgi::kTileTma : hgi::kTileAuto);
@@ -210,11 +281,12 @@ int run_tile_path(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images,
         c_q = a.s_q;
         cw = a.wD;
         ch = a.hD;
+        cpitch = a.dpitch;
     }
     return HGI_OK;
 }
 
-int run_level_path(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images, uint32_t w, uint32_t h,
+int run_level_path(hgi_ctx* ctx, Scratch& sc, int mode, const uint8_t* src, uint32_t n_images, uint32_t w, uint32_t h,
                    uint32_t levels, const hgi_params_t* prm, uint8_t* grid_out, uint8_t* recon_out,
                    cudaStream_t st)
 {
@@ -228,9 +300,9 @@ int run_level_path(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images
         per = (uint32_t)(budget / plane);
         if (per < 1) per = 1;
         if (per > n_images) per = n_images;
-        int rc = reserve(ctx, ctx->level_recon, (size_t)per * plane);
+        int rc = reserve(ctx, sc.level_recon, (size_t)per * plane);
         if (rc) return rc;
-        recon = ctx->level_recon.p;
+        recon = sc.level_recon.p;
     }
     for (uint32_t first = 0; first < n_images; first += per) {
         const uint32_t cnt = (n_images - first < per) ? n_images - first : per;
@@ -265,55 +337,62 @@ int run_level_path(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images
     return HGI_OK;
 }
 
-int run_dev(hgi_ctx* ctx, int mode, const uint8_t* src, uint32_t n_images, uint32_t w, uint32_t h,
-            const hgi_params_t* prm, uint8_t* grid_out, uint8_t* recon_out, uint32_t* hist, cudaStream_t st)
+int run_dev(hgi_ctx* ctx, Scratch& sc, int mode, const uint8_t* src, uint32_t n_images, uint32_t w, uint32_t h,
+            uint32_t pitch, const hgi_params_t* prm, uint8_t* grid_out, uint8_t* recon_out, uint32_t* hist, cudaStream_t st)
 {
-    const size_t plane = (size_t)w * h;
-    if (n_images == 0 || plane == 0) return HGI_OK;
+    if (n_images == 0 || (size_t)w * h == 0) return HGI_OK;
     const uint32_t levels = effective_levels(prm->levels, w, h);
     uint8_t* primary = (mode == hgi::kModeEncode) ? grid_out : recon_out;
-    // The residual histogram is a separate pass over the finished grid (hgi_hist_kernel): fusing the per-byte
-    // shared-memory atomics into the ALU-bound encode kernel measured slower than this pass (profiles/).
+    const bool packed = (pitch == w);
     if (levels == 0) {
         // L = 0: grid == image (src/encoder.rs:26-37 copies every pixel, the level loop is empty)
-        HGI_CUDA(ctx, cudaMemcpyAsync(primary, src, (size_t)n_images * plane, cudaMemcpyDeviceToDevice, st));
+        HGI_CUDA(ctx, cudaMemcpy2DAsync(primary, pitch, src, pitch, w, (size_t)h * n_images, cudaMemcpyDeviceToDevice, st));
         if (mode == hgi::kModeEncode && recon_out)
-            HGI_CUDA(ctx, cudaMemcpyAsync(recon_out, src, (size_t)n_images * plane, cudaMemcpyDeviceToDevice, st));
+            HGI_CUDA(ctx, cudaMemcpy2DAsync(recon_out, pitch, src, pitch, w, (size_t)h * n_images, cudaMemcpyDeviceToDevice, st));
     } else if (ctx->path == HGI_PATH_PER_LEVEL) {  // all other paths are tile variants
-        int rc = run_level_path(ctx, mode, src, n_images, w, h, levels, prm, grid_out, recon_out, st);
+        if (!packed) return HGI_ERR_UNSUPPORTED;    // the per-level kernels address packed planes only
+        int rc = run_level_path(ctx, sc, mode, src, n_images, w, h, levels, prm, grid_out, recon_out, st);
         if (rc) return rc;
     } else {
-        int rc = run_tile_path(ctx, mode, src, n_images, w, h, levels, prm, grid_out, recon_out, st);
+        int rc = run_tile_path(ctx, sc, mode, src, n_images, w, h, pitch, levels, prm, grid_out, recon_out, st);
         if (rc) return rc;
     }
     if (hist) {
-        HGI_CUDA(ctx, hgi::launch_histogram(grid_out, plane, n_images, hist, st));
+        // The residual histogram is a pass of its own over the finished grid (hgi_hist_kernel)
+        HGI_CUDA(ctx, hgi::launch_histogram(grid_out, w, h, pitch, n_images, hist, st));
         ctx->launches++;
     }
     return HGI_OK;
 }
 
-bool plane_size_ok(uint32_t w, uint32_t h, uint32_t n_images)
+// Limits of the kernels' 32-bit offset arithmetic (tile-relative offsets up to 64 rows * pitch): rows shorter than 2^26
+// bytes; the per-image residual histogram has 32-bit bins.
+constexpr uint32_t kMaxPitch = 1u << 26;
+
+bool plane_size_ok(uint32_t w, uint32_t h, uint32_t n_images, uint32_t pitch = 0)
 {
-    const unsigned __int128 total = (unsigned __int128)w * h * n_images;
+    if (pitch == 0) pitch = w;
+    if (pitch < w || pitch >= kMaxPitch) return false;
+    const unsigned __int128 total = (unsigned __int128)pitch * h * n_images;
     return total < ((unsigned __int128)1 << 62);
 }
 
 // Host-pointer batch driver: images are cut into chunks that flow through `kSlots` stream slots
 // (H2D -> kernels -> D2H), so copies in both directions overlap the kernels.
-int run_host(hgi_ctx* ctx, int mode, const uint8_t* in, uint32_t n_images, uint32_t w, uint32_t h,
-             const hgi_params_t* prm, uint8_t* out, uint8_t* recon_out, uint32_t* hist_out)
+int run_host_chunks(hgi_ctx* ctx, int mode, const uint8_t* in, uint32_t n_images, uint32_t w, uint32_t h,
+                    const hgi_params_t* prm, uint8_t* out, uint8_t* recon_out, uint32_t* hist_out, int* used_out)
 {
     const size_t plane = (size_t)w * h;
-    if (n_images == 0 || plane == 0) return HGI_OK;
     uint32_t per = (uint32_t)(chunk_bytes() / plane);
     if (per < 1) per = 1;
     if (per > n_images) per = n_images;
     const uint32_t n_chunks = (n_images + per - 1) / per;
-    const int used = n_chunks < (uint32_t)kSlots ? (int)n_chunks : kSlots;
+    const int nslots = slot_count();
+    const int used = n_chunks < (uint32_t)nslots ? (int)n_chunks : nslots;
     for (int s = 0; s < used; ++s) {
         Slot& sl = ctx->slots[s];
         if (!sl.stream) HGI_CUDA(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        *used_out = s + 1;
         int rc = reserve(ctx, sl.in, (size_t)per * plane);
         if (!rc) rc = reserve(ctx, sl.out, (size_t)per * plane);
         if (!rc && recon_out) rc = reserve(ctx, sl.aux, (size_t)per * plane);
@@ -327,15 +406,15 @@ int run_host(hgi_ctx* ctx, int mode, const uint8_t* in, uint32_t n_images, uint3
         }
     }
     for (uint32_t c = 0; c < n_chunks; ++c) {
-        Slot& sl = ctx->slots[c % kSlots];
+        Slot& sl = ctx->slots[c % (uint32_t)used];
         const uint32_t first = c * per;
         const uint32_t cnt = (n_images - first < per) ? n_images - first : per;
         const size_t off = (size_t)first * plane, bytes = (size_t)cnt * plane;
-        // stream order on the slot protects its buffers from the previous chunk that used them
+        // stream order on the slot protects its buffers and its scratch planes from the previous chunk that used them
         HGI_CUDA(ctx, cudaMemcpyAsync(sl.in.p, in + off, bytes, cudaMemcpyHostToDevice, sl.stream));
         uint8_t* d_grid = (mode == hgi::kModeEncode) ? sl.out.p : nullptr;
         uint8_t* d_recon = (mode == hgi::kModeEncode) ? (recon_out ? sl.aux.p : nullptr) : sl.out.p;
-        int rc = run_dev(ctx, mode, sl.in.p, cnt, w, h, prm, d_grid, d_recon, hist_out ? sl.hist : nullptr, sl.stream);
+        int rc = run_dev(ctx, sl.scratch, mode, sl.in.p, cnt, w, h, w, prm, d_grid, d_recon, hist_out ? sl.hist : nullptr, sl.stream);
         if (rc) return rc;
         HGI_CUDA(ctx, cudaMemcpyAsync(out + off, sl.out.p, bytes, cudaMemcpyDeviceToHost, sl.stream));
         if (mode == hgi::kModeEncode && recon_out)
@@ -344,8 +423,24 @@ int run_host(hgi_ctx* ctx, int mode, const uint8_t* in, uint32_t n_images, uint3
             HGI_CUDA(ctx, cudaMemcpyAsync(hist_out + (size_t)first * 256, sl.hist, (size_t)cnt * 256 * sizeof(uint32_t),
                                           cudaMemcpyDeviceToHost, sl.stream));
     }
-    for (int s = 0; s < used; ++s) HGI_CUDA(ctx, cudaStreamSynchronize(ctx->slots[s].stream));
     return HGI_OK;
+}
+
+// Host-pointer batch driver: images are cut into chunks that flow through the stream slots (H2D -> kernels -> D2H),
+// so copies in both directions overlap the kernels.  Whatever happens, no copy into the caller's buffers is still in
+// flight when this returns: the slot streams are drained on the error path too.
+int run_host(hgi_ctx* ctx, int mode, const uint8_t* in, uint32_t n_images, uint32_t w, uint32_t h,
+             const hgi_params_t* prm, uint8_t* out, uint8_t* recon_out, uint32_t* hist_out)
+{
+    if (n_images == 0 || (size_t)w * h == 0) return HGI_OK;
+    int used = 0;
+    int rc = run_host_chunks(ctx, mode, in, n_images, w, h, prm, out, recon_out, hist_out, &used);
+    for (int s = 0; s < used; ++s) {
+        const cudaError_t e = cudaStreamSynchronize(ctx->slots[s].stream);
+        if (e != cudaSuccess && rc == HGI_OK) rc = fail(ctx, e);   // the first error is the one reported
+    }
+    if (rc != HGI_OK) (void)cudaGetLastError();
+    return rc;
 }
 
 }  // namespace
@@ -406,9 +501,11 @@ void hgi_ctx_destroy(hgi_ctx_t* ctx)
     {
         DeviceGuard g(ctx);
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-        for (auto& b : ctx->compact) if (b.p) cudaFree(b.p);
-        if (ctx->level_recon.p) cudaFree(ctx->level_recon.p);
+        (void)cudaDeviceSynchronize();   // caller streams may still run chains that use the scratch sets
+        for (StreamScratch* ss : ctx->caller_scratch) { free_scratch(ss->scratch); delete ss; }
+        ctx->caller_scratch.clear();
         for (auto& s : ctx->slots) {
+            free_scratch(s.scratch);
             if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
             if (s.in.p) cudaFree(s.in.p);
             if (s.out.p) cudaFree(s.out.p);
@@ -457,36 +554,54 @@ int hgi_quant_table(int quant_kind, int quant_level, uint8_t table_out[256], uin
     return HGI_OK;
 }
 
-int hgi_encode_dev(hgi_ctx_t* ctx, const uint8_t* d_images, uint32_t n_images, uint32_t width, uint32_t height,
-                   const hgi_params_t* params, uint8_t* d_grids_out, uint8_t* d_recon_out, uint32_t* d_hist_out,
-                   void* stream)
+int hgi_encode_dev_pitched(hgi_ctx_t* ctx, const uint8_t* d_images, uint32_t n_images, uint32_t width, uint32_t height,
+                           uint32_t pitch, const hgi_params_t* params, uint8_t* d_grids_out, uint8_t* d_recon_out,
+                           uint32_t* d_hist_out, void* stream)
 {
     if (!ctx) return HGI_ERR_INVALID_ARG;
     int rc = check_params(params, true);
     if (rc) return rc;
-    if (!plane_size_ok(width, height, n_images)) return HGI_ERR_INVALID_ARG;
+    if (!plane_size_ok(width, height, n_images, pitch)) return HGI_ERR_INVALID_ARG;
+    if (d_hist_out && (uint64_t)width * height >= (1ull << 32)) return HGI_ERR_INVALID_ARG;   // u32 bins
     if ((size_t)width * height * n_images == 0) return HGI_OK;
     if (!d_images || !d_grids_out) return HGI_ERR_INVALID_ARG;
     DeviceGuard g(ctx);
     if (!g.ok) return HGI_ERR_CUDA;
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-    return run_dev(ctx, hgi::kModeEncode, d_images, n_images, width, height, params, d_grids_out, d_recon_out,
+    Scratch* sc = scratch_for(ctx, st);
+    if (!sc) return HGI_ERR_ALLOC;
+    return run_dev(ctx, *sc, hgi::kModeEncode, d_images, n_images, width, height, pitch, params, d_grids_out, d_recon_out,
                    d_hist_out, st);
 }
 
-int hgi_decode_dev(hgi_ctx_t* ctx, const uint8_t* d_grids, uint32_t n_images, uint32_t width, uint32_t height,
-                   const hgi_params_t* params, uint8_t* d_images_out, void* stream)
+int hgi_decode_dev_pitched(hgi_ctx_t* ctx, const uint8_t* d_grids, uint32_t n_images, uint32_t width, uint32_t height,
+                           uint32_t pitch, const hgi_params_t* params, uint8_t* d_images_out, void* stream)
 {
     if (!ctx) return HGI_ERR_INVALID_ARG;
     int rc = check_params(params, false);
     if (rc) return rc;
-    if (!plane_size_ok(width, height, n_images)) return HGI_ERR_INVALID_ARG;
+    if (!plane_size_ok(width, height, n_images, pitch)) return HGI_ERR_INVALID_ARG;
     if ((size_t)width * height * n_images == 0) return HGI_OK;
     if (!d_grids || !d_images_out) return HGI_ERR_INVALID_ARG;
     DeviceGuard g(ctx);
     if (!g.ok) return HGI_ERR_CUDA;
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-    return run_dev(ctx, hgi::kModeDecode, d_grids, n_images, width, height, params, nullptr, d_images_out, nullptr, st);
+    Scratch* sc = scratch_for(ctx, st);
+    if (!sc) return HGI_ERR_ALLOC;
+    return run_dev(ctx, *sc, hgi::kModeDecode, d_grids, n_images, width, height, pitch, params, nullptr, d_images_out, nullptr, st);
+}
+
+int hgi_encode_dev(hgi_ctx_t* ctx, const uint8_t* d_images, uint32_t n_images, uint32_t width, uint32_t height,
+                   const hgi_params_t* params, uint8_t* d_grids_out, uint8_t* d_recon_out, uint32_t* d_hist_out,
+                   void* stream)
+{
+    return hgi_encode_dev_pitched(ctx, d_images, n_images, width, height, width, params, d_grids_out, d_recon_out, d_hist_out, stream);
+}
+
+int hgi_decode_dev(hgi_ctx_t* ctx, const uint8_t* d_grids, uint32_t n_images, uint32_t width, uint32_t height,
+                   const hgi_params_t* params, uint8_t* d_images_out, void* stream)
+{
+    return hgi_decode_dev_pitched(ctx, d_grids, n_images, width, height, width, params, d_images_out, stream);
 }
 
 int hgi_histogram_dev(hgi_ctx_t* ctx, const uint8_t* d_grid, size_t n_per_image, uint32_t n_images,
@@ -499,7 +614,7 @@ int hgi_histogram_dev(hgi_ctx_t* ctx, const uint8_t* d_grid, size_t n_per_image,
     DeviceGuard g(ctx);
     if (!g.ok) return HGI_ERR_CUDA;
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-    HGI_CUDA(ctx, hgi::launch_histogram(d_grid, n_per_image, n_images, d_hist_out, st));
+    HGI_CUDA(ctx, hgi::launch_histogram(d_grid, (uint32_t)n_per_image, 1u, (uint32_t)n_per_image, n_images, d_hist_out, st));
     ctx->launches++;
     return HGI_OK;
 }
@@ -612,7 +727,7 @@ int hgi_histogram_u8(hgi_ctx_t* ctx, const uint8_t* grid, size_t n, uint64_t his
     if (!g.ok) return HGI_ERR_CUDA;
     Slot& sl = ctx->slots[0];
     if (!sl.stream) HGI_CUDA(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-    const size_t chunk = (size_t)1 << 30;  // keeps the u32 device bins far from overflow
+    const size_t chunk = (size_t)1 << 30;  // keeps the u32 device bins far from overflow (and the length a uint32_t)
     int rc = reserve(ctx, sl.in, n < chunk ? n : chunk);
     if (rc) return rc;
     if (sl.hist_cap < 256) {
@@ -626,7 +741,7 @@ int hgi_histogram_u8(hgi_ctx_t* ctx, const uint8_t* grid, size_t n, uint64_t his
     for (size_t off = 0; off < n; off += chunk) {
         const size_t len = (n - off < chunk) ? n - off : chunk;
         HGI_CUDA(ctx, cudaMemcpyAsync(sl.in.p, grid + off, len, cudaMemcpyHostToDevice, sl.stream));
-        HGI_CUDA(ctx, hgi::launch_histogram(sl.in.p, len, 1, sl.hist, sl.stream));
+        HGI_CUDA(ctx, hgi::launch_histogram(sl.in.p, (uint32_t)len, 1u, (uint32_t)len, 1, sl.hist, sl.stream));
         ctx->launches++;
         HGI_CUDA(ctx, cudaMemcpyAsync(part, sl.hist, sizeof(part), cudaMemcpyDeviceToHost, sl.stream));
         HGI_CUDA(ctx, cudaStreamSynchronize(sl.stream));

@@ -22,7 +22,11 @@ struct PassArgs {
     const uint8_t* c_q;      // compact symbols of the coarser pass (encode, non-top)
     uint8_t* s_recon;        // D>1: compact reconstruction written by this pass (wD x hD)
     uint8_t* s_q;            // D>1, encode: compact symbols written by this pass
+    uint8_t* dec_in;         // D>1: scratch for the decimated source (this pass's lattice as a dense plane, pitch dpitch)
     uint32_t w, h;           // full-resolution plane size
+    uint32_t pitch;          // bytes per row of src / grid_out / recon_out (>= w; == w for the reference's packed planes)
+    uint32_t cpitch;         // bytes per row of c_recon / c_q
+    uint32_t dpitch;         // D>1: bytes per row of s_recon / s_q / dec_in (16-byte multiple)
     uint32_t wD, hD;         // lattice size of this pass: ceil(w/D), ceil(h/D)
     uint32_t cw, ch;         // size of the coarser pass's compact planes
     uint32_t d_log2;         // log2(D)
@@ -32,10 +36,6 @@ struct PassArgs {
     uint32_t n_images;
     uint32_t quant_error;    // 0 => identity quantizer
     uint32_t vec_ok;         // D==1 and rows are 16-byte aligned => 128-bit global accesses
-    // source addressing of the SWAR kernel's lattice view (filled by launch_tile_pass_fast): byte distance between
-    // horizontally / vertically adjacent lattice points and between images in `src`
-    uint32_t src_xstride;
-    uint64_t src_pitch, src_plane;
     // SWAR quantizer constants (quant_swar() of hgi_tile_swar.cuh, evaluated on the host per launch)
     uint32_t q_one, q_mul, q_add, q_shift, q_scale, q_rmask, q_qmul;
     uint32_t q_hK, q_hc1, q_hS, q_hc2;   // fp16x2 form
@@ -64,12 +64,18 @@ struct LevelArgs {
     uint32_t n_images;
     uint32_t quant_error;
 };
+// D>1 passes of the SWAR kernels: gather the pass's lattice {multiples of 2^d_log2} of `n_images` pitched planes into
+// dense planes (dpitch x hD each, zero padded), so that the pass itself runs on contiguous rows.
+cudaError_t launch_decimate(const uint8_t* src, uint32_t pitch, uint32_t h, uint32_t d_log2, uint32_t wD, uint32_t hD,
+                            uint32_t dpitch, uint32_t n_images, uint8_t* dst, cudaStream_t stream);
 cudaError_t launch_seed(int mode, const uint8_t* src, uint8_t* dst, uint32_t w, uint32_t h,
                         uint32_t levels, uint32_t n_images, cudaStream_t stream);
 cudaError_t launch_level(int mode, int interp, const LevelArgs& args, cudaStream_t stream);
 
 // ---- reductions ---------------------------------------------------------------------------
-cudaError_t launch_histogram(const uint8_t* data, size_t n_per_image, uint32_t n_images,
+// `n_images` planes of `h` rows of `w` bytes, `pitch` bytes apart (pitch == w: one contiguous run of w * h bytes per
+// image); hist_out[img][256] is overwritten.
+cudaError_t launch_histogram(const uint8_t* data, uint32_t w, uint32_t h, uint32_t pitch, uint32_t n_images,
                              uint32_t* hist_out, cudaStream_t stream);
 cudaError_t launch_rgb_to_luma(const uint8_t* rgb, size_t n_pixels, uint8_t* luma, cudaStream_t stream);
 cudaError_t launch_error_metrics(const uint8_t* before, const uint8_t* after, size_t n,

@@ -12,58 +12,93 @@ namespace {
 
 constexpr int HT = 256;
 
-// Each block owns a contiguous slice of one image.  Bins live in shared memory as lane-private columns,
-// cell(bin, lane) = bins[bin * 32 + lane], so the 32 lanes of a warp always hit 32 different banks: every
-// shared-memory atomic is one conflict-free wavefront whatever the symbol statistics (a residual plane is mostly
-// zeros, the worst case for per-warp bins).  The eight warps of the block share the columns; a final pass sums
-// each bin over its 32 lanes with warp shuffles and issues one global atomic per non-empty bin per block.
-__device__ __forceinline__ void hist_count_word(uint32_t* col, uint32_t w)
+// Residual histogram.  Each block owns a slice of one image (a contiguous byte range of a packed plane, a range of
+// rows of a pitched one) and counts it into PRIVATE bins in shared memory: one column of 256 counters per lane,
+// cell(bin, lane) at byte offset bin * 256 + lane * 4, so the 32 lanes of a warp always hit 32 different banks --
+// every update is one conflict-free wavefront whatever the symbol statistics (a residual plane is mostly one symbol,
+// the worst case for bins shared inside a warp; partially merged or partially predicated updates are 2.5x slower on
+// this machine than full conflict-free ones, tools/ubench_hist.cu).  The 256-byte bin stride (half of it padding,
+// 64 KB per block) makes the cell's offset ONE byte permute of the data word and the lane constant, [lane*4, byte k,
+// 0, 0], used directly as the address of the update: two instructions per byte (PRMT + the update, 1.2 clocks per
+// 32 bytes per SM against 2.6 with the 128-byte stride that needs a multiply-add), which moves the kernel from the
+// shared-memory update rate to the HBM roofline.  The eight warps of a block share the columns; the updates are
+// fire-and-forget increments of the shared-memory unit (no value returns, no retry loop).  The unit slows down when
+// many lanes of one instruction fall into the same 128-byte row (24 of 32 lanes: 3.8 clocks instead of 2.6), which is
+// exactly what a mostly-zero residual plane does to bin 0; so lane l keeps bin b in row b ^ (8 * l): equal symbols
+// of different lanes land in 32 different rows, at the price of one XOR per four bytes.  At the end the block sums
+// each bin over its 32 lanes with warp shuffles and issues one global RED per non-empty bin.
+constexpr int kHistBinStride = 256;                         // bytes between bins
+constexpr int kHistSmem = 256 * kHistBinStride;             // 64 KB
+__device__ __forceinline__ void hist_count_word(uint8_t* bins, uint32_t w, uint32_t lane4)
 {
-    atomicAdd(col + ((w & 0xFFu) << 5), 1u);
-    atomicAdd(col + ((w >> 3) & 0x1FE0u), 1u);      // ((w >> 8) & 0xFF) << 5
-    atomicAdd(col + ((w >> 11) & 0x1FE0u), 1u);     // ((w >> 16) & 0xFF) << 5
-    atomicAdd(col + ((w >> 19) & 0x1FE0u), 1u);     // (w >> 24) << 5
+#ifndef HGI_VAR_HIST_NOSWZ
+    w ^= lane4 * 0x02020202u;   // row = bin ^ (8 * lane): equal symbols of different lanes go to different rows (see below)
+#endif
+    atomicAdd(reinterpret_cast<uint32_t*>(bins + __byte_perm(w, lane4, 0x6504u)), 1u);
+    atomicAdd(reinterpret_cast<uint32_t*>(bins + __byte_perm(w, lane4, 0x6514u)), 1u);
+    atomicAdd(reinterpret_cast<uint32_t*>(bins + __byte_perm(w, lane4, 0x6524u)), 1u);
+    atomicAdd(reinterpret_cast<uint32_t*>(bins + __byte_perm(w, lane4, 0x6534u)), 1u);
+}
+__device__ __forceinline__ void hist_count_byte(uint8_t* bins, uint32_t b, uint32_t lane4)
+{
+#ifndef HGI_VAR_HIST_NOSWZ
+    b ^= 2u * lane4;
+#endif
+    atomicAdd(reinterpret_cast<uint32_t*>(bins + b * kHistBinStride + lane4), 1u);
+}
+
+// one contiguous run of `len` bytes: byte head up to 16-byte alignment, 128-bit body (two loads in flight), byte tail
+__device__ __forceinline__ void hist_count_run(const uint8_t* __restrict__ p, size_t len, uint8_t* bins, uint32_t lane4, int tid)
+{
+    size_t head = ((16 - ((uintptr_t)p & 15)) & 15);
+    if (head > len) head = len;
+    for (size_t i = tid; i < head; i += HT) hist_count_byte(bins, p[i], lane4);
+    const size_t nvec = (len - head) / 16;
+    const uint4* v4 = reinterpret_cast<const uint4*>(p + head);
+    size_t i = tid;
+    for (; i + HT < nvec; i += 2 * HT) {
+        const uint4 v0 = __ldg(v4 + i), v1 = __ldg(v4 + i + HT);
+        hist_count_word(bins, v0.x, lane4); hist_count_word(bins, v0.y, lane4); hist_count_word(bins, v0.z, lane4); hist_count_word(bins, v0.w, lane4);
+        hist_count_word(bins, v1.x, lane4); hist_count_word(bins, v1.y, lane4); hist_count_word(bins, v1.z, lane4); hist_count_word(bins, v1.w, lane4);
+    }
+    for (; i < nvec; i += HT) {
+        const uint4 v = __ldg(v4 + i);
+        hist_count_word(bins, v.x, lane4); hist_count_word(bins, v.y, lane4); hist_count_word(bins, v.z, lane4); hist_count_word(bins, v.w, lane4);
+    }
+    for (size_t j = head + nvec * 16 + tid; j < len; j += HT) hist_count_byte(bins, p[j], lane4);
 }
 
 __global__ void __launch_bounds__(HT)
-hgi_hist_kernel(const uint8_t* __restrict__ data, size_t n_per_image, uint32_t blocks_per_image,
+hgi_hist_kernel(const uint8_t* __restrict__ data, uint32_t w, uint32_t h, uint32_t pitch, uint32_t blocks_per_image,
                 uint32_t* __restrict__ hist)
 {
-    __shared__ uint32_t bins[256 * 32];             // 32 KB
+    extern __shared__ __align__(256) uint8_t bins[];   // kHistSmem bytes
     const int tid = threadIdx.x, lane = tid & 31;
-    for (int i = tid; i < 256 * 32; i += HT) bins[i] = 0u;
+    const uint32_t lane4 = 4u * (uint32_t)lane;
+    for (int i = tid; i < 256 * 32; i += HT) *reinterpret_cast<uint32_t*>(bins + (i >> 5) * kHistBinStride + 4 * (i & 31)) = 0u;
     __syncthreads();
     const uint32_t img = blockIdx.x / blocks_per_image;
     const uint32_t b = blockIdx.x - img * blocks_per_image;
-    const uint8_t* base = data + (size_t)img * n_per_image;
-    const size_t per_block = ((n_per_image + blocks_per_image - 1) / blocks_per_image + 15) & ~(size_t)15;
-    size_t lo = (size_t)b * per_block, hi = lo + per_block;
-    if (hi > n_per_image) hi = n_per_image;
-    uint32_t* col = bins + lane;
-    if (lo < hi) {
-        // head up to 16 B alignment, 128-bit body, byte tail
-        size_t head = ((16 - ((uintptr_t)(base + lo) & 15)) & 15);
-        if (head > hi - lo) head = hi - lo;
-        for (size_t i = lo + tid; i < lo + head; i += HT) atomicAdd(col + ((uint32_t)base[i] << 5), 1u);
-        const size_t vlo = lo + head;
-        const size_t nvec = (hi - vlo) / 16;
-        const uint4* v4 = reinterpret_cast<const uint4*>(base + vlo);
-        size_t i = tid;
-        for (; i + HT < nvec; i += 2 * HT) {        // two loads in flight per thread
-            const uint4 v0 = __ldg(v4 + i), v1 = __ldg(v4 + i + HT);
-            hist_count_word(col, v0.x); hist_count_word(col, v0.y); hist_count_word(col, v0.z); hist_count_word(col, v0.w);
-            hist_count_word(col, v1.x); hist_count_word(col, v1.y); hist_count_word(col, v1.z); hist_count_word(col, v1.w);
-        }
-        for (; i < nvec; i += HT) {
-            const uint4 v = __ldg(v4 + i);
-            hist_count_word(col, v.x); hist_count_word(col, v.y); hist_count_word(col, v.z); hist_count_word(col, v.w);
-        }
-        for (size_t j = vlo + nvec * 16 + tid; j < hi; j += HT) atomicAdd(col + ((uint32_t)base[j] << 5), 1u);
+    const uint8_t* base = data + (size_t)img * pitch * h;
+    if (pitch == w) {                               // packed plane: one run of w * h bytes, cut into 16-byte-aligned slices
+        const size_t n = (size_t)w * h;
+        const size_t per_block = ((n + blocks_per_image - 1) / blocks_per_image + 15) & ~(size_t)15;
+        size_t lo = (size_t)b * per_block, hi = lo + per_block;
+        if (hi > n) hi = n;
+        if (lo < hi) hist_count_run(base + lo, hi - lo, bins, lane4, tid);
+    } else {                                        // pitched plane: whole rows, the padding is not counted
+        const uint32_t rows = (h + blocks_per_image - 1) / blocks_per_image;
+        const uint32_t y0 = b * rows, y1 = y0 + rows < h ? y0 + rows : h;
+        for (uint32_t y = y0; y < y1; ++y) hist_count_run(base + (size_t)y * pitch, w, bins, lane4, tid);
     }
     __syncthreads();
-    // warp w reduces bins [32w, 32w+32): lane-parallel reads of one bin row, shuffle tree
+    // warp k reduces bins [32k, 32k+32): lane-parallel reads of one bin row, shuffle tree
     for (int bin = (tid >> 5) * 32; bin < (tid >> 5) * 32 + 32; ++bin) {
-        uint32_t v = bins[bin * 32 + lane];
+#ifndef HGI_VAR_HIST_NOSWZ
+        uint32_t v = *reinterpret_cast<const uint32_t*>(bins + (bin ^ (int)(2u * lane4)) * kHistBinStride + lane4);
+#else
+        uint32_t v = *reinterpret_cast<const uint32_t*>(bins + bin * kHistBinStride + lane4);
+#endif
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
         if (lane == 0 && v) atomicAdd(&hist[(size_t)img * 256 + bin], v);
@@ -183,17 +218,25 @@ cudaError_t launch_rgb_to_luma(const uint8_t* rgb, size_t n_pixels, uint8_t* lum
     return cudaGetLastError();
 }
 
-cudaError_t launch_histogram(const uint8_t* data, size_t n_per_image, uint32_t n_images,
+cudaError_t launch_histogram(const uint8_t* data, uint32_t w, uint32_t h, uint32_t pitch, uint32_t n_images,
                              uint32_t* hist_out, cudaStream_t stream)
 {
     if (n_images == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(hist_out, 0, (size_t)n_images * 256 * sizeof(uint32_t), stream);
+    const uint64_t n_per_image = (uint64_t)w * h;
     if (e != cudaSuccess || n_per_image == 0) return e;
-    // ~64 KiB per block, but at least enough blocks to fill the chip for a single big plane
-    uint64_t bpi = (n_per_image + 65535) / 65536;
+    // Zeroing and reducing the 32 KB of counters costs a block about as much as counting 32 KB of data: give every
+    // block 256 KiB when the job is large, and not less than 32 KiB (a single small plane still spreads over the chip)
+    static const cudaError_t attr = cudaFuncSetAttribute(hgi_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem);
+    if (attr != cudaSuccess) return attr;
+    const uint64_t total = n_per_image * n_images;
+    const uint64_t per_block = total >= (512ull << 20) ? (256u << 10) : (total >= (32ull << 20) ? (64u << 10) : (32u << 10));
+    uint64_t bpi = (n_per_image + per_block - 1) / per_block;
     if (bpi < 1) bpi = 1;
+    if (pitch != w && bpi > h) bpi = h;
     if (bpi * n_images > 0x7FFFFFFFull) bpi = 0x7FFFFFFFull / n_images;
-    hgi_hist_kernel<<<(uint32_t)(bpi * n_images), HT, 0, stream>>>(data, n_per_image, (uint32_t)bpi, hist_out);
+    if (bpi < 1) return cudaErrorInvalidConfiguration;
+    hgi_hist_kernel<<<(uint32_t)(bpi * n_images), HT, kHistSmem, stream>>>(data, w, h, pitch, (uint32_t)bpi, hist_out);
     return cudaGetLastError();
 }
 

@@ -23,9 +23,12 @@
 //    branch in the light kernels, a launch of its own for the quantizing encode (instruction-cache footprint);
 //  * the shared-memory window base is pinned in a register (opaque_smem);
 //  * EXTRA instantiations also write the reconstruction plane;
-//  * instantiations: ALIGNED (w % 16 == 0, 16-byte bases: 128-bit accesses) or any width / base alignment
-//    (32-bit accesses, funnel-shifted when rows are not 4-byte aligned, bytes at the ragged right edge); STRIDED
-//    (a D > 1 pass as a lattice view: strided gathers in, compact planes out).
+//  * instantiations: ALIGNED (row pitch % 16 == 0, 16-byte bases: 128-bit accesses; the width itself may be anything
+//    when the caller pads its rows) or any pitch / base alignment (32-bit accesses, funnel-shifted when rows are not
+//    4-byte aligned, bytes at the ragged right edge);
+//  * a D > 1 pass (levels coarser than 16) first gathers its lattice into a dense plane (hgi_decimate_kernel, coalesced)
+//    and then runs this same kernel on it: the strided in-kernel gather it replaces cost 16 us per pass on a
+//    16384^2 plane against 4 us for the dense tile.
 //
 // Reference semantics: src/encoder.rs:39-71, src/decoder.rs:18-46, src/utils.rs:11-41,
 // src/interpolator.rs:15-28,41-91, src/quantizator.rs:41-74.
@@ -67,7 +70,18 @@ __device__ __forceinline__ uint4 load_chunk(const uint8_t* __restrict__ ptr, int
 {
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (nvalid <= 0) return v;
-    if (ALIGNED) return __ldg(reinterpret_cast<const uint4*>(ptr));
+    if (ALIGNED) {
+        // padded rows: the chunk is in memory as a whole, bytes beyond the image are the caller's padding -> read as 0
+        uint4 a = __ldg(reinterpret_cast<const uint4*>(ptr));
+        if (nvalid < 16) {
+            const uint32_t nb = (uint32_t)nvalid;
+            a.x &= nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
+            a.y &= nb >= 8 ? 0xFFFFFFFFu : (nb <= 4 ? 0u : ((1u << (8 * (nb - 4))) - 1u));
+            a.z &= nb >= 12 ? 0xFFFFFFFFu : (nb <= 8 ? 0u : ((1u << (8 * (nb - 8))) - 1u));
+            a.w &= nb <= 12 ? 0u : ((1u << (8 * (nb - 12))) - 1u);
+        }
+        return a;
+    }
     const uint32_t sh = (uint32_t)((uintptr_t)ptr & 3u);
     if (nvalid >= 16 && (sh == 0 || may_overread)) {
         const uint32_t* q = reinterpret_cast<const uint32_t*>(ptr - sh);
@@ -81,16 +95,6 @@ __device__ __forceinline__ uint4 load_chunk(const uint8_t* __restrict__ ptr, int
 #pragma unroll
     for (int i = 0; i < 16; ++i)
         if (i < nvalid) w[i >> 2] |= (uint32_t)__ldg(ptr + i) << (8 * (i & 3));
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-// Strided gather of one chunk for the D > 1 passes (lattice points are `xs` bytes apart in the plane).
-__device__ __forceinline__ uint4 load_chunk_strided(const uint8_t* __restrict__ ptr, int nvalid, uint32_t xs)
-{
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-        if (i < nvalid) w[i >> 2] |= (uint32_t)__ldg(ptr + (size_t)i * xs) << (8 * (i & 3));
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
@@ -139,7 +143,7 @@ __device__ __forceinline__ FastSmem& opaque_smem(FastSmem& s)
 
 // EDGE = false: the tile and its whole halo lie inside the image, so every extent is a compile-time constant
 // and all the in-image predicates (loads, stores, fringe cells, masks) fold away.
-template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED, bool STRIDED, bool EDGE>
+template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED, bool EDGE>
 __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint32_t tx, uint32_t ty)
 {
     constexpr int F = 1 << NLEV;
@@ -152,11 +156,9 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     const int xin = EDGE ? (int)min((uint32_t)(TW + FMAX + 1), p.w - X0) : TW + FMAX + 1;   // in-image extent of tile + halo
     const int yin = EDGE ? (int)min((uint32_t)(TH + FMAX + 1), p.h - Y0) : TH + FMAX + 1;
     const bool edge = EDGE;
-    const size_t tile_off = ((size_t)img * p.h + Y0) * p.w + X0;     // CTA-uniform; offset in the output planes
-    const uint32_t xs = STRIDED ? p.src_xstride : 1u;                // source strides (bytes)
-    const size_t pitch = STRIDED ? (size_t)p.src_pitch : (size_t)p.w;
-    const uint8_t* __restrict__ tile = STRIDED ? p.src + (size_t)img * p.src_plane + (size_t)Y0 * pitch + (size_t)X0 * xs
-                                               : p.src + tile_off;
+    const size_t tile_off = ((size_t)img * p.h + Y0) * p.pitch + X0;   // CTA-uniform; the same in the source and output planes
+    const size_t pitch = (size_t)p.pitch;
+    const uint8_t* __restrict__ tile = p.src + tile_off;
     const bool top = (p.c_recon == nullptr);
     const QuantSwar qc = {p.q_one, p.q_mul, p.q_add, p.q_shift, p.q_scale, p.q_rmask, p.q_qmul, p.q_hK, p.q_hc1, p.q_hS, p.q_hc2};   // filled by the launcher
 
@@ -165,22 +167,16 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     const int nvalid = max(0, min(16, xin - 16 * sx));   // in-image bytes of this thread's chunks (0 or 16 if ALIGNED)
     // a thread's NU units are vertically adjacent row pairs (rp = NU*ry + u): the corner row between two units is
     // unpacked once and shared (A/B measured ~3 % faster than units RPB row pairs apart)
-    const uint32_t toff = (uint32_t)(2 * NU * ry) * p.w + (uint32_t)(16 * sx);   // tile-relative, fits 32 bits
+    const uint32_t toff = (uint32_t)(2 * NU * ry) * p.pitch + (uint32_t)(16 * sx);   // tile-relative, fits 32 bits (pitch < 2^26)
     uint4 ev[NU], od[NU];
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
         const int y = 2 * (NU * ry + u);
         // a complete chunk may be over-read by <= 3 bytes unless it ends the very last row of the batch
-        const bool last0 = EDGE && (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 1 >= p.h) && (X0 + 16u * sx + 16u >= p.w);
-        const bool last1 = EDGE && (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 2 >= p.h) && (X0 + 16u * sx + 16u >= p.w);
-        if (STRIDED) {
-            const uint8_t* r0 = tile + (size_t)y * pitch + (size_t)(16 * sx) * xs;
-            ev[u] = load_chunk_strided(r0, y < yin ? nvalid : 0, xs);
-            od[u] = load_chunk_strided(r0 + pitch, y + 1 < yin ? nvalid : 0, xs);
-        } else {
-            ev[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * u) * p.w, y < yin ? nvalid : 0, !last0);
-            od[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * u + 1) * p.w, y + 1 < yin ? nvalid : 0, !last1);
-        }
+        const bool last0 = EDGE && (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 1 >= p.h) && (X0 + 16u * sx + 16u >= p.pitch);
+        const bool last1 = EDGE && (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 2 >= p.h) && (X0 + 16u * sx + 16u >= p.pitch);
+        ev[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * u) * p.pitch, y < yin ? nvalid : 0, !last0);
+        od[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * u + 1) * p.pitch, y + 1 < yin ? nvalid : 0, !last1);
     }
 
     // halo chunks (right of / below the tile) feed only the coarse planes; the upper half of the CTA
@@ -196,10 +192,7 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     const bool halo = NLEV > 1 && hj >= 0 && hj < NHALO;
     uint4 hv = make_uint4(0u, 0u, 0u, 0u);
     if (halo && hy < yin) {
-        if (STRIDED)
-            hv = load_chunk_strided(tile + (size_t)hy * pitch + (size_t)(16 * hc) * xs, min(16, xin - 16 * hc), xs);
-        else
-            hv = load_chunk<ALIGNED>(tile + (uint32_t)hy * p.w + (uint32_t)(16 * hc), min(16, xin - 16 * hc), false);
+        hv = load_chunk<ALIGNED>(tile + (uint32_t)hy * p.pitch + (uint32_t)(16 * hc), min(16, xin - 16 * hc), false);
     }
 
     // ---- 2. stage the dense coarse planes + the coarse lattice of this pass ---------------------
@@ -235,7 +228,7 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
             const int cj = tid <= last_cj ? tid : last_cj;
             const int x = ci * 16, y = cj * 16;
             uint8_t rv = 0;
-            if (x < xin && y < yin) rv = __ldg(tile + (size_t)y * pitch + (size_t)x * xs);
+            if (x < xin && y < yin) rv = __ldg(tile + (size_t)y * pitch + (size_t)x);
             Pf[cj * pf + ci] = rv;
             if (MODE == kModeEncode) Qf[cj * pf + ci] = rv;
         }
@@ -250,10 +243,10 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
             uint8_t rv = 0, qv = 0;
             if (x < xin && y < yin) {
                 if (top) {   // src/encoder.rs:26-37 / src/decoder.rs:22-28: the seed is the source byte
-                    rv = __ldg(tile + (size_t)y * pitch + (size_t)x * xs);
+                    rv = __ldg(tile + (size_t)y * pitch + (size_t)x);
                     qv = rv;
                 } else {
-                    const size_t co = (size_t)img * p.cw * p.ch + (size_t)((Y0 + y) >> NLEV) * p.cw + ((X0 + x) >> NLEV);
+                    const size_t co = ((size_t)img * p.ch + ((Y0 + y) >> NLEV)) * p.cpitch + ((X0 + x) >> NLEV);
                     rv = __ldg(p.c_recon + co);
                     if (MODE == kModeEncode) qv = __ldg(p.c_q + co);
                 }
@@ -271,8 +264,8 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
             uint4 e_ = ev[u], d_ = od[u];                                                                             \
             e_.x ^= (extra);                                                                                          \
             const int y_ = 2 * (NU * ry + u);                                                                         \
-            if (nvalid > 0 && y_ < yin) *reinterpret_cast<uint4*>(o_ + toff + (uint32_t)(2 * u) * p.w) = e_;          \
-            if (nvalid > 0 && y_ + 1 < yin) *reinterpret_cast<uint4*>(o_ + toff + (uint32_t)(2 * u + 1) * p.w) = d_;  \
+            if (nvalid > 0 && y_ < yin) *reinterpret_cast<uint4*>(o_ + toff + (uint32_t)(2 * u) * p.pitch) = e_;          \
+            if (nvalid > 0 && y_ + 1 < yin) *reinterpret_cast<uint4*>(o_ + toff + (uint32_t)(2 * u + 1) * p.pitch) = d_;  \
         }                                                                                                             \
         return;                                                                                                       \
     }
@@ -310,7 +303,7 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     for (int u = 0; u < NU; ++u) {
         const int rp = NU * ry + u;
         const bool row0_ok = 2 * rp < yin, row1_ok = 2 * rp + 1 < yin;
-        const uint32_t uoff = toff + (uint32_t)(2 * u) * p.w;
+        const uint32_t uoff = toff + (uint32_t)(2 * u) * p.pitch;
         if (u > 0) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) { A[k] = B[k]; C[k] = D[k]; }
@@ -349,21 +342,19 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
             }
         }
         store_chunk<ALIGNED>(out + uoff, out_ev, row0_ok ? nvalid : 0);
-        store_chunk<ALIGNED>(out + uoff + p.w, out_od, row1_ok ? nvalid : 0);
+        store_chunk<ALIGNED>(out + uoff + p.pitch, out_od, row1_ok ? nvalid : 0);
         if (MODE == kModeEncode && EXTRA) {
             if (p.recon_out != nullptr) {
                 uint8_t* __restrict__ rout = p.recon_out + tile_off;
                 store_chunk<ALIGNED>(rout + uoff, rec_ev, row0_ok ? nvalid : 0);
-                store_chunk<ALIGNED>(rout + uoff + p.w, rec_od, row1_ok ? nvalid : 0);
+                store_chunk<ALIGNED>(rout + uoff + p.pitch, rec_od, row1_ok ? nvalid : 0);
             }
         }
     }
 }
 
-// STRIDED: a D > 1 pass -- p.w / p.h are the lattice dimensions, pixels are gathered with the src_* strides and the
-// results go to the compact planes (grid_out = symbols, recon_out = reconstruction, both with pitch p.w).
-template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED, bool STRIDED>
-__global__ void __launch_bounds__(NT, (IDENTITY && !EXTRA && ALIGNED && !STRIDED && NLEV == 4) ? HGI_FAST_MIN_BLOCKS_LIGHT : HGI_FAST_MIN_BLOCKS)
+template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED>
+__global__ void __launch_bounds__(NT, (IDENTITY && !EXTRA && ALIGNED && NLEV == 4) ? HGI_FAST_MIN_BLOCKS_LIGHT : HGI_FAST_MIN_BLOCKS)
 hgi_tile_fast_kernel(const PassArgs p)
 {
     __shared__ FastSmem sm_static;
@@ -371,27 +362,27 @@ hgi_tile_fast_kernel(const PassArgs p)
     // interior tiles (88 % of a 1080p plane) take the predicate-free body; only the headline instantiations of the
     // light kernels are split this way -- the quantizing encode is split at launch level instead (below): with both
     // bodies in one kernel its code is 43 KB and it runs 12 % slower, an instruction-cache effect
-    constexpr bool kSplit = ((MODE == kModeDecode) || IDENTITY) && ALIGNED && !STRIDED && NLEV == 4;
+    constexpr bool kSplit = ((MODE == kModeDecode) || IDENTITY) && ALIGNED && NLEV == 4;
     if (kSplit) {
         const bool interior = (blockIdx.x + 1) * TW + FMAX + 1 <= p.w && (blockIdx.y + 1) * TH + FMAX + 1 <= p.h;
         if (interior) {
-            tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, STRIDED, false>(p, sm, blockIdx.x, blockIdx.y);
+            tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, false>(p, sm, blockIdx.x, blockIdx.y);
             return;
         }
     }
-    tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, STRIDED, true>(p, sm, blockIdx.x, blockIdx.y);
+    tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, true>(p, sm, blockIdx.x, blockIdx.y);
 }
 
 // The same pass as two launches: PART 1 = the interior tiles [0, fast_itx) x [0, fast_ity) with the predicate-free
 // body, PART 2 = the remaining bottom rows and right columns of tiles, enumerated along blockIdx.x.
-template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED, bool STRIDED, int PART>
-__global__ void __launch_bounds__(NT, (IDENTITY && !EXTRA && ALIGNED && !STRIDED && NLEV == 4) ? HGI_FAST_MIN_BLOCKS_LIGHT : HGI_FAST_MIN_BLOCKS)
+template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED, int PART>
+__global__ void __launch_bounds__(NT, (IDENTITY && !EXTRA && ALIGNED && NLEV == 4) ? HGI_FAST_MIN_BLOCKS_LIGHT : HGI_FAST_MIN_BLOCKS)
 hgi_tile_fast_part_kernel(const PassArgs p)
 {
     __shared__ FastSmem sm_static;
     FastSmem& sm = opaque_smem(sm_static);
     if (PART == 1) {
-        tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, STRIDED, false>(p, sm, blockIdx.x, blockIdx.y);
+        tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, false>(p, sm, blockIdx.x, blockIdx.y);
     } else {
         const uint32_t idx = blockIdx.x, nright = (p.fast_tx - p.fast_itx) * p.fast_ity;
         uint32_t tx, ty;
@@ -403,14 +394,14 @@ hgi_tile_fast_part_kernel(const PassArgs p)
             ty = p.fast_ity + j / p.fast_tx;
             tx = j - (j / p.fast_tx) * p.fast_tx;
         }
-        tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, STRIDED, true>(p, sm, tx, ty);
+        tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, true>(p, sm, tx, ty);
     }
 }
 
 // below this many tiles (about four waves of 10 CTAs on 148 SMs) the second launch costs more than the edge predicates
 constexpr uint64_t kSplitMinTiles = 4 * 1480;
 
-template <int MODE, int INTERP, bool EXTRA, int NLEV, bool ALIGNED, bool STRIDED>
+template <int MODE, int INTERP, bool EXTRA, int NLEV, bool ALIGNED>
 cudaError_t launch_fast_split(PassArgs& a, uint32_t tiles_x, uint32_t tiles_y, cudaStream_t stream)
 {
     a.fast_tx = tiles_x;
@@ -419,50 +410,50 @@ cudaError_t launch_fast_split(PassArgs& a, uint32_t tiles_x, uint32_t tiles_y, c
     if (a.fast_itx == 0 || a.fast_ity == 0) a.fast_itx = a.fast_ity = 0;
     if (a.fast_itx) {
         const dim3 nb(a.fast_itx, a.fast_ity, a.n_images);
-        hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, STRIDED, 1><<<nb, NT, 0, stream>>>(a); ++launch_count();
+        hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 1><<<nb, NT, 0, stream>>>(a); ++launch_count();
     }
     const uint32_t nedge = tiles_x * tiles_y - a.fast_itx * a.fast_ity;
     if (nedge) {
         const dim3 nb(nedge, 1, a.n_images);
-        hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, STRIDED, 2><<<nb, NT, 0, stream>>>(a); ++launch_count();
+        hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 2><<<nb, NT, 0, stream>>>(a); ++launch_count();
     }
     return cudaGetLastError();
 }
 
-template <int MODE, int INTERP, int NLEV, bool ALIGNED, bool STRIDED>
+template <int MODE, int INTERP, int NLEV, bool ALIGNED>
 cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
 {
     const uint32_t tiles_x = (args.w + TW - 1) / TW, tiles_y = (args.h + TH - 1) / TH;
     if (tiles_x == 0 || tiles_y == 0 || args.n_images == 0) return cudaSuccess;
     if (tiles_y > 65535u) return cudaErrorInvalidConfiguration;
-    const size_t plane = (size_t)args.w * args.h;
+    const size_t plane = (size_t)args.pitch * args.h;
     for (uint32_t first = 0; first < args.n_images; first += 65535u) {   // gridDim.z limit
         PassArgs a = args;
         a.n_images = args.n_images - first < 65535u ? args.n_images - first : 65535u;
-        a.src = args.src + (size_t)first * (STRIDED ? (size_t)args.src_plane : plane);
+        a.src = args.src + (size_t)first * plane;
         if (args.grid_out) a.grid_out = args.grid_out + (size_t)first * plane;
         if (args.recon_out) a.recon_out = args.recon_out + (size_t)first * plane;
-        if (args.c_recon) a.c_recon = args.c_recon + (size_t)first * args.cw * args.ch;
-        if (args.c_q) a.c_q = args.c_q + (size_t)first * args.cw * args.ch;
+        if (args.c_recon) a.c_recon = args.c_recon + (size_t)first * args.cpitch * args.ch;
+        if (args.c_q) a.c_q = args.c_q + (size_t)first * args.cpitch * args.ch;
         const dim3 nb(tiles_x, tiles_y, a.n_images);
         if (MODE == kModeDecode) {
-            hgi_tile_fast_kernel<kModeDecode, INTERP, true, false, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a); ++launch_count();
+            hgi_tile_fast_kernel<kModeDecode, INTERP, true, false, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a); ++launch_count();
         } else {
             const bool extra = (a.recon_out != nullptr);
             const bool ident = (a.quant_error == 0);
-            if (ident && !extra) { hgi_tile_fast_kernel<kModeEncode, INTERP, true, false, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
-            else if (ident) { hgi_tile_fast_kernel<kModeEncode, INTERP, true, true, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
-            else if constexpr (ALIGNED && !STRIDED && NLEV == 4 && MODE == kModeEncode) {
+            if (ident && !extra) { hgi_tile_fast_kernel<kModeEncode, INTERP, true, false, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
+            else if (ident) { hgi_tile_fast_kernel<kModeEncode, INTERP, true, true, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
+            else if constexpr (ALIGNED && NLEV == 4 && MODE == kModeEncode) {
                 if ((uint64_t)tiles_x * tiles_y * a.n_images >= kSplitMinTiles) {
-                    const cudaError_t es = extra ? launch_fast_split<kModeEncode, INTERP, true, NLEV, ALIGNED, STRIDED>(a, tiles_x, tiles_y, stream)
-                                                 : launch_fast_split<kModeEncode, INTERP, false, NLEV, ALIGNED, STRIDED>(a, tiles_x, tiles_y, stream);
+                    const cudaError_t es = extra ? launch_fast_split<kModeEncode, INTERP, true, NLEV, ALIGNED>(a, tiles_x, tiles_y, stream)
+                                                 : launch_fast_split<kModeEncode, INTERP, false, NLEV, ALIGNED>(a, tiles_x, tiles_y, stream);
                     if (es != cudaSuccess) return es;
                 }   // small jobs: one launch, less latency
-                else if (!extra) { hgi_tile_fast_kernel<kModeEncode, INTERP, false, false, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
-                else { hgi_tile_fast_kernel<kModeEncode, INTERP, false, true, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
+                else if (!extra) { hgi_tile_fast_kernel<kModeEncode, INTERP, false, false, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
+                else { hgi_tile_fast_kernel<kModeEncode, INTERP, false, true, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
             }
-            else if (!extra) { hgi_tile_fast_kernel<kModeEncode, INTERP, false, false, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
-            else { hgi_tile_fast_kernel<kModeEncode, INTERP, false, true, NLEV, ALIGNED, STRIDED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
+            else if (!extra) { hgi_tile_fast_kernel<kModeEncode, INTERP, false, false, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
+            else { hgi_tile_fast_kernel<kModeEncode, INTERP, false, true, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
         }
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -475,38 +466,34 @@ cudaError_t launch_fast_t(const PassArgs& args_in, cudaStream_t stream)
 {
     PassArgs a = args_in;
     fill_quant_args(a);
-    if (a.d_log2 > 0) {   // coarse pass: lattice view of the planes, compact outputs
+    if (a.d_log2 > 0) {   // coarse pass: gather the lattice into a dense plane, then an ordinary pass on it -> compact outputs
+        const cudaError_t e = launch_decimate(a.src, a.pitch, a.h, a.d_log2, a.wD, a.hD, a.dpitch, a.n_images, a.dec_in, stream);
+        if (e != cudaSuccess) return e;
         PassArgs v = a;
+        v.src = a.dec_in;
         v.w = a.wD;
         v.h = a.hD;
-        v.src_xstride = 1u << a.d_log2;
-        v.src_pitch = (uint64_t)a.w << a.d_log2;
-        v.src_plane = (uint64_t)a.w * a.h;
+        v.pitch = a.dpitch;
         v.grid_out = a.s_q;
         v.recon_out = a.s_recon;
-        v.vec_ok = 0;
-        switch (a.nlev) {
-            case 1: return launch_fast_n<MODE, INTERP, 1, false, true>(v, stream);
-            case 2: return launch_fast_n<MODE, INTERP, 2, false, true>(v, stream);
-            case 3: return launch_fast_n<MODE, INTERP, 3, false, true>(v, stream);
-            case 4: return launch_fast_n<MODE, INTERP, 4, false, true>(v, stream);
-            default: return cudaErrorInvalidValue;
-        }
+        v.d_log2 = 0;
+        v.vec_ok = 1;         // dpitch is a 16-byte multiple and the scratch planes are cudaMalloc'ed
+        a = v;
     }
     if (a.vec_ok) {
         switch (a.nlev) {
-            case 1: return launch_fast_n<MODE, INTERP, 1, true, false>(a, stream);
-            case 2: return launch_fast_n<MODE, INTERP, 2, true, false>(a, stream);
-            case 3: return launch_fast_n<MODE, INTERP, 3, true, false>(a, stream);
-            case 4: return launch_fast_n<MODE, INTERP, 4, true, false>(a, stream);
+            case 1: return launch_fast_n<MODE, INTERP, 1, true>(a, stream);
+            case 2: return launch_fast_n<MODE, INTERP, 2, true>(a, stream);
+            case 3: return launch_fast_n<MODE, INTERP, 3, true>(a, stream);
+            case 4: return launch_fast_n<MODE, INTERP, 4, true>(a, stream);
             default: return cudaErrorInvalidValue;
         }
     }
-    switch (a.nlev) {   // any width / alignment
-        case 1: return launch_fast_n<MODE, INTERP, 1, false, false>(a, stream);
-        case 2: return launch_fast_n<MODE, INTERP, 2, false, false>(a, stream);
-        case 3: return launch_fast_n<MODE, INTERP, 3, false, false>(a, stream);
-        case 4: return launch_fast_n<MODE, INTERP, 4, false, false>(a, stream);
+    switch (a.nlev) {   // any pitch / alignment
+        case 1: return launch_fast_n<MODE, INTERP, 1, false>(a, stream);
+        case 2: return launch_fast_n<MODE, INTERP, 2, false>(a, stream);
+        case 3: return launch_fast_n<MODE, INTERP, 3, false>(a, stream);
+        case 4: return launch_fast_n<MODE, INTERP, 4, false>(a, stream);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -528,6 +515,44 @@ bool quant_swar_self_check()
         }
     }
     return true;
+}
+
+namespace {
+// dst[img][y][x] = src[img][y << d][x << d] for the lattice of a D = 2^d pass; one 32-bit word (four lattice points)
+// per thread, rows padded with zeros up to dpitch.  A warp reads 128 points 2^d bytes apart: at d = 4 that is every
+// sector of a 2 KB run, i.e. the DRAM traffic is the image rows the lattice lives on (1/16 of the plane), coalesced.
+__global__ void __launch_bounds__(256)
+hgi_decimate_kernel(const uint8_t* __restrict__ src, uint32_t pitch, uint32_t h, uint32_t d, uint32_t wD, uint32_t hD,
+                    uint32_t dpitch, uint8_t* __restrict__ dst)
+{
+    const uint32_t wx = blockIdx.x * blockDim.x + threadIdx.x;      // word index in the row
+    const uint32_t y = blockIdx.y, img = blockIdx.z;
+    if (wx * 4u >= dpitch) return;
+    const uint8_t* row = src + ((size_t)img * h + ((size_t)y << d)) * pitch;
+    uint32_t v = 0u;
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i) {
+        const uint32_t x = wx * 4u + i;
+        if (x < wD) v |= (uint32_t)__ldg(row + ((size_t)x << d)) << (8 * i);
+    }
+    *reinterpret_cast<uint32_t*>(dst + ((size_t)img * hD + y) * dpitch + 4u * wx) = v;
+}
+}  // namespace
+
+cudaError_t launch_decimate(const uint8_t* src, uint32_t pitch, uint32_t h, uint32_t d_log2, uint32_t wD, uint32_t hD,
+                            uint32_t dpitch, uint32_t n_images, uint8_t* dst, cudaStream_t stream)
+{
+    if (wD == 0 || hD == 0 || n_images == 0) return cudaSuccess;
+    if (hD > 65535u) return cudaErrorInvalidConfiguration;
+    const uint32_t words = dpitch / 4, bx = words < 256u ? ((words + 31u) / 32u) * 32u : 256u;
+    for (uint32_t first = 0; first < n_images; first += 65535u) {
+        const uint32_t cnt = n_images - first < 65535u ? n_images - first : 65535u;
+        const dim3 nb((words + bx - 1) / bx, hD, cnt);
+        hgi_decimate_kernel<<<nb, bx, 0, stream>>>(src + (size_t)first * pitch * h, pitch, h, d_log2, wD, hD, dpitch,
+                                                   dst + (size_t)first * dpitch * hD);
+        ++launch_count();
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t launch_tile_pass_fast(int mode, int interp, const PassArgs& a, cudaStream_t stream)

@@ -91,21 +91,23 @@ hgi_tile_kernel(const PassArgs p)
     const int X0 = (int)(tx * TW), Y0 = (int)(ty * TH);       // lattice coordinates of the tile
     const int xin = (int)min((uint32_t)(TW + FMAX + 1), p.wD - (uint32_t)X0);  // in-image extent
     const int yin = (int)min((uint32_t)(TH + FMAX + 1), p.hD - (uint32_t)Y0);
-    const size_t plane = (size_t)p.w * p.h;
+    const size_t plane = (size_t)p.pitch * p.h;   // full-resolution planes: rows of p.pitch bytes
     const uint8_t* __restrict__ src = p.src + (size_t)img * plane;
     const bool top = (p.c_recon == nullptr);
     const int F = 1 << p.nlev;
+    // 128-bit staging only for rows that are whole chunks (with padded rows a chunk may mix pixels and padding)
+    const bool vec = p.vec_ok && (p.w & 15u) == 0;
 
     if (!IDENTITY) sm.lut[tid] = (uint8_t)quant_entry((uint32_t)tid, p.quant_error);
 
     // ---- stage the tile + halo ------------------------------------------------------------
-    if (p.vec_ok) {
+    if (vec) {
         for (int it = tid; it < LOAD_ROWS * LOAD_CHUNKS; it += NT) {
             const int ri = it / LOAD_CHUNKS, c = it - ri * LOAD_CHUNKS;
             const int r = staged_row(ri);
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (r < yin && 16 * c < xin)
-                v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(Y0 + r) * p.w + X0 + 16 * c));
+                v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(Y0 + r) * p.pitch + X0 + 16 * c));
             *reinterpret_cast<uint4*>(&sm.R[r * RPITCH + 16 * c]) = v;
         }
     } else {
@@ -114,7 +116,7 @@ hgi_tile_kernel(const PassArgs p)
             const int r = staged_row(ri);
             uint8_t v = 0;
             if (r < yin && x < xin)
-                v = __ldg(src + (((size_t)(Y0 + r)) << p.d_log2) * p.w + (((size_t)(X0 + x)) << p.d_log2));
+                v = __ldg(src + (((size_t)(Y0 + r)) << p.d_log2) * p.pitch + (((size_t)(X0 + x)) << p.d_log2));
             sm.R[r * RPITCH + x] = v;
         }
     }
@@ -130,11 +132,10 @@ hgi_tile_kernel(const PassArgs p)
             if (x < xin && y < yin) {
                 if (top) {
                     // src/encoder.rs:26-37 / src/decoder.rs:22-28: seed = the source byte itself
-                    rv = __ldg(src + (((size_t)(Y0 + y)) << p.d_log2) * p.w + (((size_t)(X0 + x)) << p.d_log2));
+                    rv = __ldg(src + (((size_t)(Y0 + y)) << p.d_log2) * p.pitch + (((size_t)(X0 + x)) << p.d_log2));
                     qv = rv;
                 } else {
-                    const size_t co = (size_t)img * p.cw * p.ch +
-                                      (size_t)((uint32_t)(Y0 + y) >> p.nlev) * p.cw + ((uint32_t)(X0 + x) >> p.nlev);
+                    const size_t co = ((size_t)img * p.ch + ((uint32_t)(Y0 + y) >> p.nlev)) * p.cpitch + ((uint32_t)(X0 + x) >> p.nlev);
                     rv = __ldg(p.c_recon + co);
                     if (MODE == kModeEncode) qv = __ldg(p.c_q + co);
                 }
@@ -165,11 +166,11 @@ hgi_tile_kernel(const PassArgs p)
     if (p.d_log2 == 0) {
         uint8_t* __restrict__ gout = (MODE == kModeEncode) ? p.grid_out + (size_t)img * plane : nullptr;
         uint8_t* __restrict__ rout = p.recon_out ? p.recon_out + (size_t)img * plane : nullptr;
-        if (p.vec_ok) {
+        if (vec) {
             for (int it = tid; it < TH * (TW / 16); it += NT) {
                 const int r = it / (TW / 16), c = it - r * (TW / 16);
                 if (r >= yout || 16 * c >= xout) continue;
-                const size_t off = (size_t)(Y0 + r) * p.w + X0 + 16 * c;
+                const size_t off = (size_t)(Y0 + r) * p.pitch + X0 + 16 * c;
                 if (MODE == kModeEncode)
                     *reinterpret_cast<uint4*>(gout + off) = *reinterpret_cast<const uint4*>(&sm.Q[r * TW + 16 * c]);
                 if (rout)
@@ -179,18 +180,18 @@ hgi_tile_kernel(const PassArgs p)
             for (int it = tid; it < TH * TW; it += NT) {
                 const int r = it / TW, x = it - r * TW;
                 if (r >= yout || x >= xout) continue;
-                const size_t off = (size_t)(Y0 + r) * p.w + X0 + x;
+                const size_t off = (size_t)(Y0 + r) * p.pitch + X0 + x;
                 if (MODE == kModeEncode) gout[off] = sm.Q[r * TW + x];
                 if (rout) rout[off] = sm.R[r * RPITCH + x];
             }
         }
     } else {
         // compact planes for the next (finer) pass
-        const size_t cbase = (size_t)img * p.wD * p.hD;
+        const size_t cbase = (size_t)img * p.dpitch * p.hD;
         for (int it = tid; it < TH * TW; it += NT) {
             const int r = it / TW, x = it - r * TW;
             if (r >= yout || x >= xout) continue;
-            const size_t off = cbase + (size_t)(Y0 + r) * p.wD + X0 + x;
+            const size_t off = cbase + (size_t)(Y0 + r) * p.dpitch + X0 + x;
             p.s_recon[off] = sm.R[r * RPITCH + x];
             if (MODE == kModeEncode) p.s_q[off] = sm.Q[r * TW + x];
         }
@@ -224,7 +225,7 @@ cudaError_t launch_tile_pass(int mode, int interp, const PassArgs& a, cudaStream
     // SWAR kernels: the prefetch kernel takes any width / alignment and, as a strided lattice view, the D > 1 passes;
     // the TMA kernel needs D == 1 and 16-byte rows.  Only planes taller than 65535 tiles stay on the generic kernel
     if (variant != kTileGeneric && (a.hD + 63) / 64 <= 65535u) {
-        if (variant == kTileTma && a.vec_ok && a.d_log2 == 0) {
+        if (variant == kTileTma && a.vec_ok && a.d_log2 == 0 && a.pitch == a.w) {
             bool used = false;
             const cudaError_t e = launch_tile_pass_tma(mode, interp, a, stream, &used);
             if (e != cudaSuccess || used) return e;

@@ -173,7 +173,7 @@ hgi_tile_tma_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
                     if (off >= 0) rv = rw[off + x];   // other rows of the over-covering fill are never read
                     qv = rv;
                 } else if (x < xin && y < yin) {
-                    const size_t co = (size_t)img * p.cw * p.ch + (size_t)((Y0 + y) >> NLEV) * p.cw + ((X0 + x) >> NLEV);
+                    const size_t co = ((size_t)img * p.ch + ((Y0 + y) >> NLEV)) * p.cpitch + ((X0 + x) >> NLEV);
                     rv = __ldg(p.c_recon + co);
                     if (MODE == kModeEncode) qv = __ldg(p.c_q + co);
                 }
