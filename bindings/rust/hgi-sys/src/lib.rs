@@ -7,6 +7,21 @@ pub struct hgi_ctx_t {
     _private: [u8; 0],
 }
 
+#[repr(C)]
+pub struct hgi_pool_t {
+    _private: [u8; 0],
+}
+
+/// One row band of `hgi_pool_plan_bands`: output rows `[y0, y1)`, input rows `[y0, in_y1)`.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, PartialEq, Eq)]
+pub struct hgi_band_t {
+    pub y0: u32,
+    pub y1: u32,
+    pub in_y1: u32,
+}
+
+pub const HGI_ABI_VERSION: c_int = 2;
 pub const HGI_OK: c_int = 0;
 pub const HGI_ERR_INVALID_ARG: c_int = -1;
 pub const HGI_ERR_NO_DEVICE: c_int = -2;
@@ -51,6 +66,7 @@ extern "C" {
     pub fn hgi_ctx_last_cuda_error(ctx: *const hgi_ctx_t) -> c_int;
     pub fn hgi_ctx_last_cuda_error_string(ctx: *const hgi_ctx_t) -> *const c_char;
     pub fn hgi_ctx_kernel_launches(ctx: *const hgi_ctx_t) -> u64;
+    pub fn hgi_ctx_graph_launches(ctx: *const hgi_ctx_t) -> u64;
     pub fn hgi_quant_table(kind: c_int, level: c_int, table_out: *mut u8, error_out: *mut u8) -> c_int;
     pub fn hgi_encode_u8(ctx: *mut hgi_ctx_t, image: *const u8, width: u32, height: u32, params: *const hgi_params_t,
                          grid_out: *mut u8, recon_out: *mut u8) -> c_int;
@@ -81,6 +97,26 @@ extern "C" {
                              d_hist_out: *mut u32, stream: *mut c_void) -> c_int;
     pub fn hgi_error_metrics_dev(ctx: *mut hgi_ctx_t, d_before: *const u8, d_after: *const u8, n: usize,
                                  d_out: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn hgi_pool_create(devices: *const c_int, n_devices: c_int, pool_out: *mut *mut hgi_pool_t) -> c_int;
+    pub fn hgi_pool_destroy(pool: *mut hgi_pool_t);
+    pub fn hgi_pool_size(pool: *const hgi_pool_t) -> c_int;
+    pub fn hgi_pool_ctx(pool: *mut hgi_pool_t, index: c_int) -> *mut hgi_ctx_t;
+    pub fn hgi_pool_device(pool: *const hgi_pool_t, index: c_int) -> c_int;
+    pub fn hgi_pool_synchronize(pool: *mut hgi_pool_t) -> c_int;
+    pub fn hgi_pool_encode_batch_u8(pool: *mut hgi_pool_t, images: *const u8, n_images: u32, width: u32, height: u32,
+                                    params: *const hgi_params_t, grids_out: *mut u8, hist_out: *mut u32) -> c_int;
+    pub fn hgi_pool_decode_batch_u8(pool: *mut hgi_pool_t, grids: *const u8, n_images: u32, width: u32, height: u32,
+                                    params: *const hgi_params_t, images_out: *mut u8) -> c_int;
+    pub fn hgi_pool_plan_bands(pool: *const hgi_pool_t, height: u32, levels: u32, bands_out: *mut hgi_band_t,
+                               n_bands_out: *mut c_int) -> c_int;
+    pub fn hgi_pool_encode_plane_u8(pool: *mut hgi_pool_t, image: *const u8, width: u32, height: u32,
+                                    params: *const hgi_params_t, grid_out: *mut u8) -> c_int;
+    pub fn hgi_pool_decode_plane_u8(pool: *mut hgi_pool_t, grid: *const u8, width: u32, height: u32,
+                                    params: *const hgi_params_t, image_out: *mut u8) -> c_int;
+    pub fn hgi_pool_encode_bands_dev(pool: *mut hgi_pool_t, d_bands_in: *const *const u8, width: u32, height: u32,
+                                     params: *const hgi_params_t, d_bands_out: *const *mut u8) -> c_int;
+    pub fn hgi_pool_decode_bands_dev(pool: *mut hgi_pool_t, d_bands_in: *const *const u8, width: u32, height: u32,
+                                     params: *const hgi_params_t, d_bands_out: *const *mut u8) -> c_int;
     pub fn hgi_archive_bound(n: usize) -> usize;
     pub fn hgi_archive_serialize(m: *const hgi_metadata_t, grid: *const u8, grid_len: usize, grid_width: u64,
                                  out: *mut u8, out_capacity: usize, out_len: *mut usize) -> c_int;

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HGI_ABI_VERSION 1
+#define HGI_ABI_VERSION 2
 
 typedef struct hgi_ctx hgi_ctx_t;
 
@@ -104,8 +104,12 @@ int hgi_ctx_synchronize(hgi_ctx_t *ctx);
 /* cudaError_t of the last failing runtime call (0 if none) and its string. */
 int hgi_ctx_last_cuda_error(const hgi_ctx_t *ctx);
 const char *hgi_ctx_last_cuda_error_string(const hgi_ctx_t *ctx);
-/* Number of kernels this context has launched since creation (monotonic). */
+/* Number of kernels this context has launched since creation (monotonic; kernels replayed from a captured
+   launch chain count too), and how many of its device-API calls were served by one graph launch: identical
+   consecutive `*_dev` calls whose chain has three or more kernels (levels > 4) are captured once and replayed
+   (HGI_B200_GRAPHS=0 in the environment turns this off). */
 uint64_t hgi_ctx_kernel_launches(const hgi_ctx_t *ctx);
+uint64_t hgi_ctx_graph_launches(const hgi_ctx_t *ctx);
 
 /* ---- quantizator ------------------------------------------------------------------------ */
 /* `Linear::from(level)` / `NoOp::from(level)` (src/quantizator.rs:19-23,41-63): fills the
@@ -177,6 +181,51 @@ int hgi_decode_dev_pitched(hgi_ctx_t *ctx, const uint8_t *d_grids, uint32_t n_im
 /* d_out[0] = sum of squares, d_out[1] = max abs (both u64, overwritten). */
 int hgi_error_metrics_dev(hgi_ctx_t *ctx, const uint8_t *d_before, const uint8_t *d_after,
                           size_t n, uint64_t *d_out, void *stream);
+
+/* ---- pool: the GPUs of one box behind one handle ------------------------------------------ */
+/* The reference encodes one image per call on one thread (benches/bench.rs:54-110, src/main.rs:41-71); the path
+   shards with no exchange between the shards, so a pool drives one context per GPU from the calling
+   thread: work is enqueued on every device before anything is waited for.  Results are byte-identical to a single
+   context.  For overlap of the copies pass pinned (page-locked) host buffers. */
+typedef struct hgi_pool hgi_pool_t;
+/* `devices` = CUDA device ordinals (a device may appear more than once: several contexts on it);
+   n_devices == 0 => every sm_100 device of the box. */
+int hgi_pool_create(const int *devices, int n_devices, hgi_pool_t **pool_out);
+void hgi_pool_destroy(hgi_pool_t *pool);
+int hgi_pool_size(const hgi_pool_t *pool);
+hgi_ctx_t *hgi_pool_ctx(hgi_pool_t *pool, int index);   /* the pool keeps ownership */
+int hgi_pool_device(const hgi_pool_t *pool, int index); /* CUDA ordinal of member `index` */
+int hgi_pool_synchronize(hgi_pool_t *pool);
+/* By image: member k encodes/decodes the k-th contiguous share of the batch (`Encoder::encode` / `Decoder::decode`
+   over n_images planes, src/encoder.rs:39-71, src/decoder.rs:18-46).  Host pointers; returns when all results are
+   in the output buffers. */
+int hgi_pool_encode_batch_u8(hgi_pool_t *pool, const uint8_t *images, uint32_t n_images, uint32_t width,
+                             uint32_t height, const hgi_params_t *params, uint8_t *grids_out,
+                             uint32_t *hist_out /* [n_images][256] or NULL */);
+int hgi_pool_decode_batch_u8(hgi_pool_t *pool, const uint8_t *grids, uint32_t n_images, uint32_t width,
+                             uint32_t height, const hgi_params_t *params, uint8_t *images_out);
+/* By row band: ONE plane cut into at most hgi_pool_size() bands whose heights are multiples of S = 2^levels.
+   Band [y0, y1) is computed by its member from the input rows [y0, in_y1), in_y1 = min(height, y1 + S + 1):
+   the prediction of a cell reads only its own corners at floor and floor + step (src/interpolator.rs:67-73), so
+   dependencies point right/down and the rows below a band are recomputed instead of exchanged. */
+typedef struct {
+    uint32_t y0, y1; /* output rows [y0, y1) */
+    uint32_t in_y1;  /* input rows [y0, in_y1) */
+} hgi_band_t;
+int hgi_pool_plan_bands(const hgi_pool_t *pool, uint32_t height, uint32_t levels,
+                        hgi_band_t *bands_out /* [hgi_pool_size()] */, int *n_bands_out);
+int hgi_pool_encode_plane_u8(hgi_pool_t *pool, const uint8_t *image, uint32_t width, uint32_t height,
+                             const hgi_params_t *params, uint8_t *grid_out);
+int hgi_pool_decode_plane_u8(hgi_pool_t *pool, const uint8_t *grid, uint32_t width, uint32_t height,
+                             const hgi_params_t *params, uint8_t *image_out);
+/* The same with the bands resident on their devices: d_bands_in[k] / d_bands_out[k] are buffers on the device of
+   member k holding (in_y1 - y0) rows of `width` bytes of band k (input: the band and its overlap rows; output: rows
+   [0, y1 - y0) are the result, the overlap rows are scratch).  Enqueues on every member's own stream and returns;
+   hgi_pool_synchronize() waits.  Repeated calls with the same buffers replay one captured graph per device. */
+int hgi_pool_encode_bands_dev(hgi_pool_t *pool, const uint8_t *const *d_bands_in, uint32_t width,
+                              uint32_t height, const hgi_params_t *params, uint8_t *const *d_bands_out);
+int hgi_pool_decode_bands_dev(hgi_pool_t *pool, const uint8_t *const *d_bands_in, uint32_t width,
+                              uint32_t height, const hgi_params_t *params, uint8_t *const *d_bands_out);
 
 /* ---- archive container (src/archive.rs) -------------------------------------------------- */
 /* `Metadata` (src/archive.rs:15-22). */

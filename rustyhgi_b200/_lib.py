@@ -23,6 +23,10 @@ class Params(ctypes.Structure):
                 ("quant_kind", ctypes.c_int32), ("quant_level", ctypes.c_int32)]
 
 
+class BandStruct(ctypes.Structure):
+    _fields_ = [("y0", ctypes.c_uint32), ("y1", ctypes.c_uint32), ("in_y1", ctypes.c_uint32)]
+
+
 class MetadataStruct(ctypes.Structure):
     _fields_ = [("quantization_level", ctypes.c_uint32), ("interpolation", ctypes.c_uint32),
                 ("width", ctypes.c_uint32), ("height", ctypes.c_uint32),
@@ -44,6 +48,7 @@ PROTOTYPES = {
     "hgi_ctx_last_cuda_error": (_int, [_vp]),
     "hgi_ctx_last_cuda_error_string": (ctypes.c_char_p, [_vp]),
     "hgi_ctx_kernel_launches": (_u64, [_vp]),
+    "hgi_ctx_graph_launches": (_u64, [_vp]),
     "hgi_quant_table": (_int, [_int, _int, _vp, _vp]),
     "hgi_encode_u8": (_int, [_vp, _vp, _u32, _u32, _pp, _vp, _vp]),
     "hgi_decode_u8": (_int, [_vp, _vp, _u32, _u32, _pp, _vp]),
@@ -59,6 +64,19 @@ PROTOTYPES = {
     "hgi_decode_dev_pitched": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _pp, _vp, _vp]),
     "hgi_histogram_dev": (_int, [_vp, _vp, _sz, _u32, _vp, _vp]),
     "hgi_error_metrics_dev": (_int, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "hgi_pool_create": (_int, [_vp, _int, ctypes.POINTER(_vp)]),
+    "hgi_pool_destroy": (None, [_vp]),
+    "hgi_pool_size": (_int, [_vp]),
+    "hgi_pool_ctx": (_vp, [_vp, _int]),
+    "hgi_pool_device": (_int, [_vp, _int]),
+    "hgi_pool_synchronize": (_int, [_vp]),
+    "hgi_pool_encode_batch_u8": (_int, [_vp, _vp, _u32, _u32, _u32, _pp, _vp, _vp]),
+    "hgi_pool_decode_batch_u8": (_int, [_vp, _vp, _u32, _u32, _u32, _pp, _vp]),
+    "hgi_pool_plan_bands": (_int, [_vp, _u32, _u32, _vp, ctypes.POINTER(_int)]),
+    "hgi_pool_encode_plane_u8": (_int, [_vp, _vp, _u32, _u32, _pp, _vp]),
+    "hgi_pool_decode_plane_u8": (_int, [_vp, _vp, _u32, _u32, _pp, _vp]),
+    "hgi_pool_encode_bands_dev": (_int, [_vp, _vp, _u32, _u32, _pp, _vp]),
+    "hgi_pool_decode_bands_dev": (_int, [_vp, _vp, _u32, _u32, _pp, _vp]),
     "hgi_archive_bound": (_sz, [_sz]),
     "hgi_archive_serialize": (_int, [_pm, _vp, _sz, _u64, _vp, _sz, ctypes.POINTER(_sz)]),
     "hgi_archive_huffman_bound": (_sz, [_sz, _sz]),
@@ -66,6 +84,8 @@ PROTOTYPES = {
     "hgi_archive_read_header": (_int, [_vp, _sz, _pm]),
     "hgi_archive_read_grid": (_int, [_vp, _sz, _vp, _sz, ctypes.POINTER(_sz), ctypes.POINTER(_u64)]),
 }
+
+ABI_VERSION = 2      # HGI_ABI_VERSION of include/hgi.h
 
 _lib = None
 
@@ -82,7 +102,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError => ABI mismatch, fail loudly
             fn.restype = res
             fn.argtypes = args
-        if L.hgi_abi_version() != 1:
-            raise HgiLibraryError(f"ABI version {L.hgi_abi_version()} != 1")
+        if L.hgi_abi_version() != ABI_VERSION:
+            raise HgiLibraryError(f"ABI version {L.hgi_abi_version()} != {ABI_VERSION}")
         _lib = L
     return _lib

@@ -123,6 +123,10 @@ class Context:
     def kernel_launches(self):
         return int(_lib.lib().hgi_ctx_kernel_launches(self._h))
 
+    @property
+    def graph_launches(self):
+        return int(_lib.lib().hgi_ctx_graph_launches(self._h))
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.lib().hgi_ctx_destroy(self._h)
@@ -140,6 +144,107 @@ class Context:
             if device not in cls._defaults:
                 cls._defaults[device] = cls(device)
             return cls._defaults[device]
+
+
+class Pool:
+    """hgi_pool_t: the GPUs of one box behind one handle.  `devices` = CUDA ordinals (None: every
+    sm_100 device); a device may be listed more than once."""
+
+    def __init__(self, devices=None):
+        h = ctypes.c_void_p()
+        if devices is None:
+            rc = _lib.lib().hgi_pool_create(None, 0, ctypes.byref(h))
+        else:
+            arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+            rc = _lib.lib().hgi_pool_create(ctypes.cast(arr, ctypes.c_void_p), len(devices), ctypes.byref(h))
+        if rc:
+            raise HgiError(rc, "hgi_pool_create")
+        self._h = h
+
+    def __len__(self):
+        return int(_lib.lib().hgi_pool_size(self._h))
+
+    @property
+    def devices(self):
+        return [int(_lib.lib().hgi_pool_device(self._h, i)) for i in range(len(self))]
+
+    def _check(self, rc, where):
+        if rc:
+            raise HgiError(rc, where)
+
+    def synchronize(self):
+        self._check(_lib.lib().hgi_pool_synchronize(self._h), "hgi_pool_synchronize")
+
+    def plan_bands(self, height, levels):
+        bands = (_lib.BandStruct * max(1, len(self)))()
+        n = ctypes.c_int(0)
+        self._check(_lib.lib().hgi_pool_plan_bands(self._h, int(height), int(levels), ctypes.cast(bands, ctypes.c_void_p),
+                                                   ctypes.byref(n)), "hgi_pool_plan_bands")
+        return [(bands[i].y0, bands[i].y1, bands[i].in_y1) for i in range(n.value)]
+
+    def encode_batch(self, encoder, images, want_hist=False):
+        imgs = _host_planes(images, "images")
+        n, h, w = imgs.shape
+        grids = np.empty_like(imgs)
+        hist = np.zeros((n, 256), np.uint32) if want_hist else None
+        p = encoder._p()
+        self._check(_lib.lib().hgi_pool_encode_batch_u8(self._h, imgs.ctypes.data, n, w, h, ctypes.byref(p), grids.ctypes.data,
+                                                        hist.ctypes.data if want_hist else None), "hgi_pool_encode_batch_u8")
+        return (grids, hist) if want_hist else grids
+
+    def decode_batch(self, decoder, levels, grids):
+        g = _host_planes(grids, "grids")
+        n, h, w = g.shape
+        out = np.empty_like(g)
+        p = _params(levels, decoder._interp)
+        self._check(_lib.lib().hgi_pool_decode_batch_u8(self._h, g.ctypes.data, n, w, h, ctypes.byref(p), out.ctypes.data),
+                    "hgi_pool_decode_batch_u8")
+        return out
+
+    def encode_plane(self, encoder, image):
+        img = _host_planes(image, "image")
+        h, w = img.shape
+        grid = np.empty_like(img)
+        p = encoder._p()
+        self._check(_lib.lib().hgi_pool_encode_plane_u8(self._h, img.ctypes.data, w, h, ctypes.byref(p), grid.ctypes.data),
+                    "hgi_pool_encode_plane_u8")
+        return Grid(grid, w)
+
+    def decode_plane(self, decoder, dimensions, levels, grid):
+        width, height = int(dimensions[0]), int(dimensions[1])
+        buf = grid.buffer if isinstance(grid, Grid) else _host_planes(grid, "grid").reshape(-1)
+        out = np.empty((height, width), np.uint8)
+        p = _params(levels, decoder._interp)
+        self._check(_lib.lib().hgi_pool_decode_plane_u8(self._h, buf.ctypes.data, width, height, ctypes.byref(p), out.ctypes.data),
+                    "hgi_pool_decode_plane_u8")
+        return out
+
+    def _band_ptrs(self, tensors):
+        return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+    def encode_bands_device(self, encoder, bands_in, width, height, bands_out):
+        """bands_in[k] / bands_out[k]: CUDA uint8 tensors on the device of member k, (in_y1 - y0, width) each."""
+        p = encoder._p()
+        self._check(_lib.lib().hgi_pool_encode_bands_dev(self._h, ctypes.cast(self._band_ptrs(bands_in), ctypes.c_void_p), int(width), int(height),
+                                                         ctypes.byref(p), ctypes.cast(self._band_ptrs(bands_out), ctypes.c_void_p)),
+                    "hgi_pool_encode_bands_dev")
+
+    def decode_bands_device(self, decoder, levels, bands_in, width, height, bands_out):
+        p = _params(levels, decoder._interp)
+        self._check(_lib.lib().hgi_pool_decode_bands_dev(self._h, ctypes.cast(self._band_ptrs(bands_in), ctypes.c_void_p), int(width), int(height),
+                                                         ctypes.byref(p), ctypes.cast(self._band_ptrs(bands_out), ctypes.c_void_p)),
+                    "hgi_pool_decode_bands_dev")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().hgi_pool_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _params(levels, interp_id, quant=None):

@@ -44,6 +44,7 @@ struct DevBuf {
 // the host API, caller streams of the device API), so every stream owns its set: sharing one set let a chunk's fine
 // pass read the next chunk's coarse planes.
 struct Scratch {
+    uint64_t gen = 0;    // bumped whenever one of the buffers moves: cached launch chains that point into them are stale
     DevBuf compact[4];   // ping-pong {recon, q} compact planes of the coarse passes
     DevBuf dec_in;       // decimated source of a coarse pass
     DevBuf level_recon;  // per-level path: reconstruction planes when the caller gives none
@@ -62,6 +63,41 @@ struct StreamScratch {
     Scratch scratch;
 };
 
+// A launch chain of the device API (decimate + coarse + fine [+ edge] [+ histogram] kernels of one call), captured
+// once and replayed with one cudaGraphLaunch: what a caller with fixed buffers -- a frame loop, the band driver of
+// the pool -- pays per call on the host drops from one launch per kernel to one launch per call.
+struct ChainKey {
+    int mode, path, interp, quant_kind, quant_level;
+    const uint8_t* src;
+    uint8_t *grid_out, *recon_out;
+    uint32_t* hist;
+    uint32_t n_images, w, h, pitch, levels;
+    const Scratch* scratch;
+    uint64_t scratch_gen;
+    bool operator==(const ChainKey& o) const
+    {
+        return mode == o.mode && path == o.path && interp == o.interp && quant_kind == o.quant_kind &&
+               quant_level == o.quant_level && src == o.src && grid_out == o.grid_out && recon_out == o.recon_out &&
+               hist == o.hist && n_images == o.n_images && w == o.w && h == o.h && pitch == o.pitch &&
+               levels == o.levels && scratch == o.scratch && scratch_gen == o.scratch_gen;
+    }
+};
+struct ChainGraph {
+    ChainKey key{};
+    cudaGraphExec_t exec = nullptr;   // null: the chain was seen once and ran as plain launches
+    uint64_t launches = 0;            // kernels in the chain
+    uint64_t last_use = 0;
+};
+constexpr size_t kMaxChainGraphs = 16;
+bool graphs_enabled()
+{
+    static const bool v = [] {
+        const char* e = std::getenv("HGI_B200_GRAPHS");
+        return !(e && e[0] == '0');
+    }();
+    return v;
+}
+
 constexpr size_t kMaxCallerStreams = 32;   // scratch sets kept for device-API caller streams; the oldest is recycled
 
 }  // namespace
@@ -73,8 +109,17 @@ struct hgi_ctx {
     cudaError_t last_err = cudaSuccess;
     uint64_t launches = 0;
     std::vector<StreamScratch*> caller_scratch;   // device API: one scratch set per caller stream
+    std::vector<ChainGraph> chains;               // device API: captured launch chains (see ChainKey)
+    uint64_t chain_clock = 0, graph_launches = 0;
     Slot slots[kSlots];
     unsigned long long* d_metrics = nullptr;
+};
+
+// Several contexts (one per GPU of the box, in general) driven from one host thread: work is enqueued on every device
+// before anything is waited for (by image for batches, by row band for one huge plane).
+struct hgi_pool {
+    std::vector<hgi_ctx*> ctxs;
+    std::vector<int> used;      // slot streams with work in flight, per context
 };
 
 namespace {
@@ -151,6 +196,7 @@ Scratch* scratch_for(hgi_ctx* ctx, cudaStream_t st)
         ctx->caller_scratch.erase(ctx->caller_scratch.begin());
         (void)cudaDeviceSynchronize();
         (void)cudaGetLastError();
+        ++old->scratch.gen;              // chains captured for the old stream must not be replayed on the new one
         old->stream = st;
         ctx->caller_scratch.push_back(old);
         return &old->scratch;
@@ -160,6 +206,13 @@ Scratch* scratch_for(hgi_ctx* ctx, cudaStream_t st)
     ss->stream = st;
     ctx->caller_scratch.push_back(ss);
     return &ss->scratch;
+}
+
+int reserve(hgi_ctx* ctx, Scratch& sc, DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return HGI_OK;
+    ++sc.gen;
+    return reserve(ctx, b, bytes);
 }
 
 int check_params(const hgi_params_t* p, bool encode)
@@ -231,10 +284,10 @@ int run_tile_path(hgi_ctx* ctx, Scratch& sc, int mode, const uint8_t* src, uint3
         const int nbuf = passes.size() > 2 ? 4 : 2;
         for (int i = 0; i < nbuf; ++i) {
             if (mode == hgi::kModeDecode && (i & 1)) continue;  // decode carries no symbols
-            int rc = reserve(ctx, sc.compact[i], max_compact);
+            int rc = reserve(ctx, sc, sc.compact[i], max_compact);
             if (rc) return rc;
         }
-        int rc = reserve(ctx, sc.dec_in, max_compact);
+        int rc = reserve(ctx, sc, sc.dec_in, max_compact);
         if (rc) return rc;
     }
     const uint8_t* c_recon = nullptr;
@@ -300,7 +353,7 @@ int run_level_path(hgi_ctx* ctx, Scratch& sc, int mode, const uint8_t* src, uint
         per = (uint32_t)(budget / plane);
         if (per < 1) per = 1;
         if (per > n_images) per = n_images;
-        int rc = reserve(ctx, sc.level_recon, (size_t)per * plane);
+        int rc = reserve(ctx, sc, sc.level_recon, (size_t)per * plane);
         if (rc) return rc;
         recon = sc.level_recon.p;
     }
@@ -362,6 +415,93 @@ int run_dev(hgi_ctx* ctx, Scratch& sc, int mode, const uint8_t* src, uint32_t n_
         HGI_CUDA(ctx, hgi::launch_histogram(grid_out, w, h, pitch, n_images, hist, st));
         ctx->launches++;
     }
+    return HGI_OK;
+}
+
+void drop_chain(ChainGraph& g)
+{
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g = ChainGraph{};
+}
+
+// run_dev for the device API: identical consecutive calls (same buffers, same parameters, same stream scratch) are
+// replayed from a captured graph.  First sighting: plain launches (this also sizes the scratch planes).  Second:
+// capture + instantiate + launch.  From then on: one cudaGraphLaunch.  Chains of fewer than three launches are not
+// worth a graph; streams that are being captured by the caller, and the legacy default stream, launch directly.
+int run_dev_cached(hgi_ctx* ctx, Scratch& sc, int mode, const uint8_t* src, uint32_t n_images, uint32_t w, uint32_t h,
+                   uint32_t pitch, const hgi_params_t* prm, uint8_t* grid_out, uint8_t* recon_out, uint32_t* hist,
+                   cudaStream_t st)
+{
+    const uint32_t levels = effective_levels(prm->levels, w, h);
+    const bool multi = levels > (uint32_t)hgi::kMaxPassLevels || ctx->path == HGI_PATH_PER_LEVEL;   // >= 3 launches
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (!multi || !graphs_enabled() || st == cudaStreamLegacy || st == cudaStreamPerThread ||
+        cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+        (void)cudaGetLastError();
+        return run_dev(ctx, sc, mode, src, n_images, w, h, pitch, prm, grid_out, recon_out, hist, st);
+    }
+    ChainKey key{mode, ctx->path, prm->interp, prm->quant_kind, prm->quant_level, src, grid_out, recon_out, hist,
+                 n_images, w, h, pitch, levels, &sc, sc.gen};
+    ChainGraph* hit = nullptr;
+    for (ChainGraph& g : ctx->chains)
+        if (g.key == key) { hit = &g; break; }
+    if (hit && hit->exec) {
+        hit->last_use = ++ctx->chain_clock;
+        HGI_CUDA(ctx, cudaGraphLaunch(hit->exec, st));
+        ctx->launches += hit->launches;
+        ++ctx->graph_launches;
+        return HGI_OK;
+    }
+    if (!hit) {   // first sighting: run it plainly and remember the key (the scratch generation may move: re-key after)
+        const int rc = run_dev(ctx, sc, mode, src, n_images, w, h, pitch, prm, grid_out, recon_out, hist, st);
+        if (rc) return rc;
+        key.scratch_gen = sc.gen;
+        for (size_t i = 0; i < ctx->chains.size();)   // chains that point into moved scratch planes are dead
+            if (ctx->chains[i].key.scratch == &sc && ctx->chains[i].key.scratch_gen != sc.gen) {
+                drop_chain(ctx->chains[i]);
+                ctx->chains.erase(ctx->chains.begin() + (long)i);
+            } else ++i;
+        if (ctx->chains.size() >= kMaxChainGraphs) {
+            size_t lru = 0;
+            for (size_t i = 1; i < ctx->chains.size(); ++i)
+                if (ctx->chains[i].last_use < ctx->chains[lru].last_use) lru = i;
+            drop_chain(ctx->chains[lru]);
+            ctx->chains.erase(ctx->chains.begin() + (long)lru);
+        }
+        ChainGraph g;
+        g.key = key;
+        g.last_use = ++ctx->chain_clock;
+        ctx->chains.push_back(g);
+        return HGI_OK;
+    }
+    // second sighting: capture the chain (nothing allocates now: the first run sized every buffer)
+    const uint64_t before = ctx->launches;
+    HGI_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_dev(ctx, sc, mode, src, n_images, w, h, pitch, prm, grid_out, recon_out, hist, st);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    const uint64_t n_launch = ctx->launches - before;
+    ctx->launches = before;
+    if (rc != HGI_OK || ce != cudaSuccess || !graph || sc.gen != key.scratch_gen) {
+        if (graph) cudaGraphDestroy(graph);
+        (void)cudaGetLastError();
+        hit->last_use = ++ctx->chain_clock;
+        if (rc != HGI_OK) return rc;
+        return run_dev(ctx, sc, mode, src, n_images, w, h, pitch, prm, grid_out, recon_out, hist, st);   // capture refused: plain launches
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess || !exec) {
+        (void)cudaGetLastError();
+        return run_dev(ctx, sc, mode, src, n_images, w, h, pitch, prm, grid_out, recon_out, hist, st);
+    }
+    hit->exec = exec;
+    hit->launches = n_launch;
+    hit->last_use = ++ctx->chain_clock;
+    HGI_CUDA(ctx, cudaGraphLaunch(exec, st));
+    ctx->launches += n_launch;
+    ++ctx->graph_launches;
     return HGI_OK;
 }
 
@@ -502,6 +642,8 @@ void hgi_ctx_destroy(hgi_ctx_t* ctx)
         DeviceGuard g(ctx);
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
         (void)cudaDeviceSynchronize();   // caller streams may still run chains that use the scratch sets
+        for (ChainGraph& g : ctx->chains) drop_chain(g);
+        ctx->chains.clear();
         for (StreamScratch* ss : ctx->caller_scratch) { free_scratch(ss->scratch); delete ss; }
         ctx->caller_scratch.clear();
         for (auto& s : ctx->slots) {
@@ -542,6 +684,7 @@ const char* hgi_ctx_last_cuda_error_string(const hgi_ctx_t* ctx)
     return ctx ? cudaGetErrorString(ctx->last_err) : "";
 }
 uint64_t hgi_ctx_kernel_launches(const hgi_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t hgi_ctx_graph_launches(const hgi_ctx_t* ctx) { return ctx ? ctx->graph_launches : 0; }
 
 int hgi_quant_table(int quant_kind, int quant_level, uint8_t table_out[256], uint8_t* error_out)
 {
@@ -570,8 +713,8 @@ int hgi_encode_dev_pitched(hgi_ctx_t* ctx, const uint8_t* d_images, uint32_t n_i
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     Scratch* sc = scratch_for(ctx, st);
     if (!sc) return HGI_ERR_ALLOC;
-    return run_dev(ctx, *sc, hgi::kModeEncode, d_images, n_images, width, height, pitch, params, d_grids_out, d_recon_out,
-                   d_hist_out, st);
+    return run_dev_cached(ctx, *sc, hgi::kModeEncode, d_images, n_images, width, height, pitch, params, d_grids_out,
+                          d_recon_out, d_hist_out, st);
 }
 
 int hgi_decode_dev_pitched(hgi_ctx_t* ctx, const uint8_t* d_grids, uint32_t n_images, uint32_t width, uint32_t height,
@@ -588,7 +731,8 @@ int hgi_decode_dev_pitched(hgi_ctx_t* ctx, const uint8_t* d_grids, uint32_t n_im
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     Scratch* sc = scratch_for(ctx, st);
     if (!sc) return HGI_ERR_ALLOC;
-    return run_dev(ctx, *sc, hgi::kModeDecode, d_grids, n_images, width, height, pitch, params, nullptr, d_images_out, nullptr, st);
+    return run_dev_cached(ctx, *sc, hgi::kModeDecode, d_grids, n_images, width, height, pitch, params, nullptr, d_images_out,
+                          nullptr, st);
 }
 
 int hgi_encode_dev(hgi_ctx_t* ctx, const uint8_t* d_images, uint32_t n_images, uint32_t width, uint32_t height,
@@ -782,6 +926,274 @@ int hgi_error_metrics_u8(hgi_ctx_t* ctx, const uint8_t* before, const uint8_t* a
     if (sd_int_out) *sd_int_out = n ? total / n : 0;  // src/main.rs:106 integer division
     if (max_abs_out) *max_abs_out = (uint32_t)mx;
     return HGI_OK;
+}
+
+
+/* ---- pool: several GPUs behind one handle -------------------------------------------------------------------- */
+}  // extern "C"
+
+namespace {
+
+// Contiguous [first, last) share of `rank` out of `world` (the first n % world ranks get one more).
+void split_range(uint64_t n, uint32_t world, uint32_t rank, uint64_t* first, uint64_t* last)
+{
+    const uint64_t base = n / world, extra = n % world;
+    *first = rank * base + (rank < extra ? rank : extra);
+    *last = *first + base + (rank < extra ? 1 : 0);
+}
+
+// Bands of heights that are multiples of S = 2^levels; band [y0, y1) is bit-exact when computed from the input rows
+// [y0, min(h, y1 + S + 1)): dependencies only point right/down (src/interpolator.rs:67-73), so the rows below a band
+// are recomputed by its owner instead of being exchanged.  Empty bands are dropped.
+int plan_bands(uint32_t height, uint32_t levels, uint32_t n_bands, hgi_band_t* out)
+{
+    const uint64_t S = 1ull << (levels > 31 ? 31 : levels);
+    const uint64_t cells = (height + S - 1) / S;
+    int n = 0;
+    for (uint32_t r = 0; r < n_bands; ++r) {
+        uint64_t c0, c1;
+        split_range(cells, n_bands, r, &c0, &c1);
+        const uint64_t y0 = c0 * S < height ? c0 * S : height, y1 = c1 * S < height ? c1 * S : height;
+        if (y1 > y0) {
+            const uint64_t in_y1 = y1 + S + 1 < height ? y1 + S + 1 : height;
+            out[n++] = hgi_band_t{(uint32_t)y0, (uint32_t)y1, (uint32_t)in_y1};
+        }
+    }
+    return n;
+}
+
+int pool_wait(hgi_pool* pool, int rc)
+{
+    for (size_t d = 0; d < pool->ctxs.size(); ++d) {
+        hgi_ctx* ctx = pool->ctxs[d];
+        DeviceGuard g(ctx);
+        for (int s = 0; s < pool->used[d]; ++s) {
+            const cudaError_t e = cudaStreamSynchronize(ctx->slots[s].stream);
+            if (e != cudaSuccess && rc == HGI_OK) rc = fail(ctx, e);
+        }
+        pool->used[d] = 0;
+    }
+    if (rc != HGI_OK) (void)cudaGetLastError();
+    return rc;
+}
+
+int pool_batch(hgi_pool* pool, int mode, const uint8_t* in, uint32_t n_images, uint32_t w, uint32_t h,
+               const hgi_params_t* prm, uint8_t* out, uint32_t* hist_out)
+{
+    const size_t plane = (size_t)w * h;
+    const uint32_t world = (uint32_t)pool->ctxs.size();
+    int rc = HGI_OK;
+    for (uint32_t d = 0; d < world && rc == HGI_OK; ++d) {
+        uint64_t first, last;
+        split_range(n_images, world, d, &first, &last);
+        if (last == first) continue;
+        hgi_ctx* ctx = pool->ctxs[d];
+        DeviceGuard g(ctx);
+        if (!g.ok) { rc = HGI_ERR_CUDA; break; }
+        rc = run_host_chunks(ctx, mode, in + first * plane, (uint32_t)(last - first), w, h, prm, out + first * plane, nullptr,
+                             hist_out ? hist_out + first * 256 : nullptr, &pool->used[d]);
+    }
+    return pool_wait(pool, rc);
+}
+
+// One band on one context, host pointers: rows [y0, in_y1) in, rows [y0, y1) out; enqueued on slot 0, not waited for.
+int band_async(hgi_ctx* ctx, int mode, const uint8_t* in, uint32_t w, const hgi_band_t& b, const hgi_params_t* prm,
+               uint8_t* out, int* used)
+{
+    Slot& sl = ctx->slots[0];
+    if (!sl.stream) HGI_CUDA(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    *used = 1;
+    const size_t rows_in = b.in_y1 - b.y0, rows_out = b.y1 - b.y0;
+    int rc = reserve(ctx, sl.in, rows_in * w);
+    if (!rc) rc = reserve(ctx, sl.out, rows_in * w);
+    if (rc) return rc;
+    HGI_CUDA(ctx, cudaMemcpyAsync(sl.in.p, in + (size_t)b.y0 * w, rows_in * w, cudaMemcpyHostToDevice, sl.stream));
+    rc = run_dev(ctx, sl.scratch, mode, sl.in.p, 1, w, (uint32_t)rows_in, w, prm, mode == hgi::kModeEncode ? sl.out.p : nullptr,
+                 mode == hgi::kModeEncode ? nullptr : sl.out.p, nullptr, sl.stream);
+    if (rc) return rc;
+    HGI_CUDA(ctx, cudaMemcpyAsync(out + (size_t)b.y0 * w, sl.out.p, rows_out * w, cudaMemcpyDeviceToHost, sl.stream));
+    return HGI_OK;
+}
+
+int pool_plane(hgi_pool* pool, int mode, const uint8_t* in, uint32_t w, uint32_t h, const hgi_params_t* prm, uint8_t* out)
+{
+    std::vector<hgi_band_t> bands(pool->ctxs.size());
+    const int nb = plan_bands(h, prm->levels, (uint32_t)pool->ctxs.size(), bands.data());
+    int rc = HGI_OK;
+    for (int k = 0; k < nb && rc == HGI_OK; ++k) {
+        hgi_ctx* ctx = pool->ctxs[(size_t)k];
+        DeviceGuard g(ctx);
+        if (!g.ok) { rc = HGI_ERR_CUDA; break; }
+        rc = band_async(ctx, mode, in, w, bands[(size_t)k], prm, out, &pool->used[(size_t)k]);
+    }
+    return pool_wait(pool, rc);
+}
+
+int pool_bands_dev(hgi_pool* pool, int mode, const uint8_t* const* d_in, uint32_t w, uint32_t h, const hgi_params_t* prm,
+                   uint8_t* const* d_out)
+{
+    std::vector<hgi_band_t> bands(pool->ctxs.size());
+    const int nb = plan_bands(h, prm->levels, (uint32_t)pool->ctxs.size(), bands.data());
+    for (int k = 0; k < nb; ++k) {
+        if (!d_in[k] || !d_out[k]) return HGI_ERR_INVALID_ARG;
+        hgi_ctx* ctx = pool->ctxs[(size_t)k];
+        DeviceGuard g(ctx);
+        if (!g.ok) return HGI_ERR_CUDA;
+        Scratch* sc = scratch_for(ctx, ctx->stream);
+        if (!sc) return HGI_ERR_ALLOC;
+        const uint32_t rows_in = bands[(size_t)k].in_y1 - bands[(size_t)k].y0;
+        const int rc = run_dev_cached(ctx, *sc, mode, d_in[k], 1, w, rows_in, w, prm, mode == hgi::kModeEncode ? d_out[k] : nullptr,
+                                      mode == hgi::kModeEncode ? nullptr : d_out[k], nullptr, ctx->stream);
+        if (rc) return rc;
+    }
+    return HGI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hgi_pool_create(const int* devices, int n_devices, hgi_pool_t** pool_out)
+{
+    if (!pool_out || n_devices < 0 || (n_devices > 0 && !devices)) return HGI_ERR_INVALID_ARG;
+    *pool_out = nullptr;
+    std::vector<int> devs;
+    if (n_devices == 0) {   // every usable GPU of the box
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+            (void)cudaGetLastError();
+            return HGI_ERR_NO_DEVICE;
+        }
+        for (int d = 0; d < count; ++d) {
+            cudaDeviceProp prop{};
+            if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) devs.push_back(d);
+        }
+        if (devs.empty()) return HGI_ERR_NO_DEVICE;
+    } else {
+        devs.assign(devices, devices + n_devices);
+    }
+    hgi_pool* pool = new (std::nothrow) hgi_pool();
+    if (!pool) return HGI_ERR_ALLOC;
+    for (int d : devs) {
+        hgi_ctx* ctx = nullptr;
+        const int rc = hgi_ctx_create(d, &ctx);
+        if (rc != HGI_OK) {
+            for (hgi_ctx* c : pool->ctxs) hgi_ctx_destroy(c);
+            delete pool;
+            return rc;
+        }
+        pool->ctxs.push_back(ctx);
+    }
+    pool->used.assign(pool->ctxs.size(), 0);
+    *pool_out = pool;
+    return HGI_OK;
+}
+
+void hgi_pool_destroy(hgi_pool_t* pool)
+{
+    if (!pool) return;
+    for (hgi_ctx* c : pool->ctxs) hgi_ctx_destroy(c);
+    delete pool;
+}
+
+int hgi_pool_size(const hgi_pool_t* pool) { return pool ? (int)pool->ctxs.size() : 0; }
+
+hgi_ctx_t* hgi_pool_ctx(hgi_pool_t* pool, int index)
+{
+    return (pool && index >= 0 && (size_t)index < pool->ctxs.size()) ? pool->ctxs[(size_t)index] : nullptr;
+}
+
+int hgi_pool_device(const hgi_pool_t* pool, int index)
+{
+    return (pool && index >= 0 && (size_t)index < pool->ctxs.size()) ? pool->ctxs[(size_t)index]->device : -1;
+}
+
+int hgi_pool_synchronize(hgi_pool_t* pool)
+{
+    if (!pool) return HGI_ERR_INVALID_ARG;
+    int rc = HGI_OK;
+    for (hgi_ctx* c : pool->ctxs) {
+        const int r = hgi_ctx_synchronize(c);
+        if (r != HGI_OK && rc == HGI_OK) rc = r;
+    }
+    return rc;
+}
+
+int hgi_pool_encode_batch_u8(hgi_pool_t* pool, const uint8_t* images, uint32_t n_images, uint32_t width, uint32_t height,
+                             const hgi_params_t* params, uint8_t* grids_out, uint32_t* hist_out)
+{
+    if (!pool) return HGI_ERR_INVALID_ARG;
+    int rc = check_params(params, true);
+    if (rc) return rc;
+    if (!plane_size_ok(width, height, n_images)) return HGI_ERR_INVALID_ARG;
+    if ((size_t)width * height * n_images == 0) return HGI_OK;
+    if (!images || !grids_out) return HGI_ERR_INVALID_ARG;
+    return pool_batch(pool, hgi::kModeEncode, images, n_images, width, height, params, grids_out, hist_out);
+}
+
+int hgi_pool_decode_batch_u8(hgi_pool_t* pool, const uint8_t* grids, uint32_t n_images, uint32_t width, uint32_t height,
+                             const hgi_params_t* params, uint8_t* images_out)
+{
+    if (!pool) return HGI_ERR_INVALID_ARG;
+    int rc = check_params(params, false);
+    if (rc) return rc;
+    if (!plane_size_ok(width, height, n_images)) return HGI_ERR_INVALID_ARG;
+    if ((size_t)width * height * n_images == 0) return HGI_OK;
+    if (!grids || !images_out) return HGI_ERR_INVALID_ARG;
+    return pool_batch(pool, hgi::kModeDecode, grids, n_images, width, height, params, images_out, nullptr);
+}
+
+int hgi_pool_plan_bands(const hgi_pool_t* pool, uint32_t height, uint32_t levels, hgi_band_t* bands_out, int* n_bands_out)
+{
+    if (!pool || !bands_out || !n_bands_out || levels > HGI_MAX_LEVELS) return HGI_ERR_INVALID_ARG;
+    *n_bands_out = plan_bands(height, levels, (uint32_t)pool->ctxs.size(), bands_out);
+    return HGI_OK;
+}
+
+int hgi_pool_encode_plane_u8(hgi_pool_t* pool, const uint8_t* image, uint32_t width, uint32_t height,
+                             const hgi_params_t* params, uint8_t* grid_out)
+{
+    if (!pool) return HGI_ERR_INVALID_ARG;
+    int rc = check_params(params, true);
+    if (rc) return rc;
+    if (!plane_size_ok(width, height, 1)) return HGI_ERR_INVALID_ARG;
+    if ((size_t)width * height == 0) return HGI_OK;
+    if (!image || !grid_out) return HGI_ERR_INVALID_ARG;
+    return pool_plane(pool, hgi::kModeEncode, image, width, height, params, grid_out);
+}
+
+int hgi_pool_decode_plane_u8(hgi_pool_t* pool, const uint8_t* grid, uint32_t width, uint32_t height,
+                             const hgi_params_t* params, uint8_t* image_out)
+{
+    if (!pool) return HGI_ERR_INVALID_ARG;
+    int rc = check_params(params, false);
+    if (rc) return rc;
+    if (!plane_size_ok(width, height, 1)) return HGI_ERR_INVALID_ARG;
+    if ((size_t)width * height == 0) return HGI_OK;
+    if (!grid || !image_out) return HGI_ERR_INVALID_ARG;
+    return pool_plane(pool, hgi::kModeDecode, grid, width, height, params, image_out);
+}
+
+int hgi_pool_encode_bands_dev(hgi_pool_t* pool, const uint8_t* const* d_bands_in, uint32_t width, uint32_t height,
+                              const hgi_params_t* params, uint8_t* const* d_bands_out)
+{
+    if (!pool || !d_bands_in || !d_bands_out) return HGI_ERR_INVALID_ARG;
+    int rc = check_params(params, true);
+    if (rc) return rc;
+    if (!plane_size_ok(width, height, 1)) return HGI_ERR_INVALID_ARG;
+    if ((size_t)width * height == 0) return HGI_OK;
+    return pool_bands_dev(pool, hgi::kModeEncode, d_bands_in, width, height, params, d_bands_out);
+}
+
+int hgi_pool_decode_bands_dev(hgi_pool_t* pool, const uint8_t* const* d_bands_in, uint32_t width, uint32_t height,
+                              const hgi_params_t* params, uint8_t* const* d_bands_out)
+{
+    if (!pool || !d_bands_in || !d_bands_out) return HGI_ERR_INVALID_ARG;
+    int rc = check_params(params, false);
+    if (rc) return rc;
+    if (!plane_size_ok(width, height, 1)) return HGI_ERR_INVALID_ARG;
+    if ((size_t)width * height == 0) return HGI_OK;
+    return pool_bands_dev(pool, hgi::kModeDecode, d_bands_in, width, height, params, d_bands_out);
 }
 
 }  // extern "C"

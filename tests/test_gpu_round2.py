@@ -140,3 +140,95 @@ def test_row_length_limit(ctx):
     one = np.zeros(16, np.uint8)
     assert L.hgi_encode_dev(ctx._h, one.ctypes.data, 1, 1 << 26, 1, ctypes.byref(p), one.ctypes.data, None, None, None) == -1
     assert L.hgi_decode_dev_pitched(ctx._h, one.ctypes.data, 1, 16, 1, 8, ctypes.byref(p), one.ctypes.data, None) == -1   # pitch < width
+
+
+def _pool_devices():
+    """All visible GPUs; on a single-GPU box two contexts on device 0 (the pool logic is the same)."""
+    import torch
+    n = torch.cuda.device_count()
+    return list(range(n)) if n > 1 else [0, 0]
+
+
+def test_pool_batch_by_image_equals_the_oracle():
+    """hgi_pool_*_batch_u8: contiguous image shares on every member, with per-image histograms."""
+    pool = hgi.Pool(_pool_devices())
+    assert len(pool) >= 2
+    n, h, w, levels, q = 4 * len(pool) + 3, 270, 480, 4, 2
+    imgs = np.stack([photo_like(w, h, 5 * k + 1) for k in range(n)])
+    want_g = oc.encode_batch(imgs, levels, qlevel=q)
+    want_r = oc.decode_batch(want_g, levels)
+    enc = hgi.Encoder(hgi.Crossed, hgi.Linear(Q(q)), levels)
+    grids, hist = pool.encode_batch(enc, imgs, want_hist=True)
+    back = pool.decode_batch(hgi.Decoder(hgi.Crossed), levels, grids)
+    assert (grids == want_g).all() and (back == want_r).all()
+    for k in (0, n // 2, n - 1):
+        assert (hist[k] == np.bincount(want_g[k].reshape(-1), minlength=256)).all()
+    one = pool.encode_batch(enc, imgs[:1])            # fewer images than members: the empty shares are skipped
+    assert (one == want_g[:1]).all()
+    pool.close()
+
+
+def test_pool_row_bands_equal_the_full_plane():
+    """hgi_pool_*_plane_u8 and the device-resident band calls: bands of multiples of S rows plus S + 1 overlap rows,
+    no exchange (dependency direction: src/interpolator.rs:67-73)."""
+    import torch
+    pool = hgi.Pool(_pool_devices())
+    for (w, h, levels, q) in [(1024, 2048 + 77, 8, 2), (640, 1000, 5, 1), (333, 517, 4, 3), (256, 100, 8, 2)]:
+        img = photo_like(w, h, levels + w)
+        want_g, want_r = oc.encode(img, levels, qlevel=q, want_recon=True)
+        enc = hgi.Encoder(hgi.Crossed, hgi.Linear(Q(q)), levels)
+        dec = hgi.Decoder(hgi.Crossed)
+        grid = pool.encode_plane(enc, img)
+        assert (grid.as_plane() == want_g).all(), (w, h, levels)
+        assert (pool.decode_plane(dec, (w, h), levels, grid) == want_r).all(), (w, h, levels)
+        # device-resident bands, called three times with the same buffers: the second call captures the launch chain
+        # of every member, the third replays it
+        bands = pool.plan_bands(h, levels)
+        assert bands[0][0] == 0 and bands[-1][1] == h and all(b[0] % (1 << levels) == 0 for b in bands)
+        devs = pool.devices
+        d_in = [torch.from_numpy(img[y0:iy1]).to(f"cuda:{devs[k]}") for k, (y0, y1, iy1) in enumerate(bands)]
+        d_grid = [torch.empty_like(t) for t in d_in]
+        d_gin = [torch.from_numpy(want_g[y0:iy1]).to(f"cuda:{devs[k]}") for k, (y0, y1, iy1) in enumerate(bands)]
+        d_out = [torch.empty_like(t) for t in d_in]
+        for rep in range(3):
+            pool.encode_bands_device(enc, d_in, w, h, d_grid)
+            pool.decode_bands_device(dec, levels, d_gin, w, h, d_out)
+            pool.synchronize()
+            for k, (y0, y1, iy1) in enumerate(bands):
+                assert (d_grid[k][:y1 - y0].cpu().numpy() == want_g[y0:y1]).all(), (w, h, levels, k, rep)
+                assert (d_out[k][:y1 - y0].cpu().numpy() == want_r[y0:y1]).all(), (w, h, levels, k, rep)
+    pool.close()
+
+
+def test_launch_chains_are_replayed_from_graphs(ctx):
+    """Identical device-API calls with three or more launches (levels > 4) are captured on the second call and
+    replayed afterwards; results stay bit-exact and the kernel count keeps counting."""
+    import torch
+    w, h, levels, q = 2000, 1100, 7, 2
+    img = photo_like(w, h, 99)
+    want_g, want_r = oc.encode(img, levels, qlevel=q, want_recon=True)
+    t = torch.from_numpy(img).cuda()
+    g = torch.empty_like(t)
+    o = torch.empty_like(t)
+    st = torch.cuda.Stream()
+    enc = hgi.Encoder(hgi.Crossed, hgi.Linear(Q(q)), levels, ctx=ctx)
+    dec = hgi.Decoder(hgi.Crossed, ctx=ctx)
+    torch.cuda.synchronize()
+    g0, l0 = ctx.graph_launches, ctx.kernel_launches
+    per_call = None
+    for rep in range(5):
+        before = ctx.kernel_launches
+        enc.encode_device(t, grids_out=g, stream=st.cuda_stream)
+        if per_call is None:
+            per_call = ctx.kernel_launches - before
+        assert ctx.kernel_launches - before == per_call
+        dec.decode_device(levels, g, images_out=o, stream=st.cuda_stream)
+        st.synchronize()
+        assert (g.cpu().numpy() == want_g).all() and (o.cpu().numpy() == want_r).all(), rep
+    assert per_call >= 3
+    assert ctx.graph_launches - g0 == 2 * 4          # calls 2..5 of encode and of decode
+    # another buffer: a different chain, plain launches again, still exact
+    g2 = torch.empty_like(t)
+    enc.encode_device(t, grids_out=g2, stream=st.cuda_stream)
+    st.synchronize()
+    assert (g2.cpu().numpy() == want_g).all()
