@@ -238,6 +238,154 @@ def bind_to_gpu_numa_node(local_rank):
         return None
 
 
+def oracle_parity(frames, encs, dec, ctx, n_check=64):
+    """After the timed steps, outside the timed region: `n_check` frames spread over rank 0's shard are encoded and
+    decoded again at both quantizers and compared BYTE FOR BYTE with the oracle (grid and decoded plane)."""
+    import numpy as np
+    import torch
+    from oracle import c as oc
+    n = frames.shape[0]
+    idx = sorted(set(int(round(i * (n - 1) / max(1, n_check - 1))) for i in range(min(n_check, n))))
+    sel = torch.tensor(idx, device=frames.device)
+    sub = frames.index_select(0, sel).contiguous()
+    host = sub.cpu().numpy()
+    bad, compared = 0, 0
+    for enc, q in zip(encs, QLEVELS):
+        g = enc.encode_device(sub)
+        r = dec.decode_device(LEVELS, g)
+        torch.cuda.synchronize()
+        want_g = oc.encode_batch(host, LEVELS, qlevel=q, n_threads=oc.max_threads())
+        want_r = oc.decode_batch(want_g, LEVELS, n_threads=oc.max_threads())
+        bad += int((g.cpu().numpy() != want_g).sum()) + int((r.cpu().numpy() != want_r).sum())
+        compared += 2 * host.size
+    return {"frames_checked": len(idx), "quantizators": ["Lossless", "Medium"], "bytes_compared": compared,
+            "mismatches": bad, "checker": "oracle/hgi_oracle.c (grid bytes and decoded planes, every byte)"}
+
+
+def time_events(fn, stream, reps, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(reps):
+        fn()
+    b.record(stream)
+    b.synchronize()
+    return a.elapsed_time(b) / reps        # ms
+
+
+def per_call_us(fn, calls=200, reps=5):
+    """GPU-side cadence of `calls` back-to-back device-API calls replayed from one torch CUDA graph (no interpreter
+    between the launches): us per call."""
+    import torch
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            fn(s)
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(calls):
+                fn(s)
+        best = None
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(s)
+            g.replay()
+            b.record(s)
+            b.synchronize()
+            t = a.elapsed_time(b) * 1e3 / calls
+            best = t if best is None else min(best, t)
+    torch.cuda.current_stream().wait_stream(s)
+    return best
+
+
+def extra_block(hgi, ctx, dev, rank, world, dist, peak, grids_medium, barrier):
+    """Numbers the headline line does not carry: single planes (configs[1..3] per call), configs[3] (16384^2, level 8,
+    Medium) on one GPU and as row bands over the ranks, and the residual histogram -- all device-resident."""
+    import torch
+    Qm = hgi.QuantizationLevel
+    out = {}
+    stream = torch.cuda.current_stream(dev)
+    # ---- residual histogram over this rank's Medium grids: 1 B/byte read
+    n = grids_medium.shape[0]
+    hist = torch.empty((n, 256), dtype=torch.int32, device=dev)
+    L = hgi.lib()
+    sth = stream.cuda_stream or 1
+    ms = time_events(lambda: ctx.check(L.hgi_histogram_dev(ctx._h, grids_medium.data_ptr(), H * W, n, hist.data_ptr(), sth), "hist"), stream, 10)
+    assert int(hist[0].sum().item()) == H * W
+    gbs = n * H * W / (ms * 1e-3) / 1e9
+    out["histogram"] = {"kernel": "hgi_hist_kernel (256-bin per image, private per-lane columns in shared memory)",
+                        "frames": n, "ms": ms, "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                                                           "frac": gbs / peak, "algorithmic_bytes_per_byte": 1.0}}
+    if rank == 0:
+        # ---- single planes, us per device-resident call (configs[1]: 1920x1080 L4; configs[2] size: 2368x2614 L6 High)
+        single = {}
+        for name, (w, h, lv, q) in {"c2_1080p_L4_lossless": (1920, 1080, 4, 0), "c2_1080p_L4_medium": (1920, 1080, 4, 2),
+                                    "c3_2368x2614_L6_high": (2368, 2614, 6, 3)}.items():
+            yy = torch.arange(h, device=dev, dtype=torch.int32)[:, None]
+            xx = torch.arange(w, device=dev, dtype=torch.int32)[None, :]
+            img = ((xx * yy) & 255).to(torch.uint8).contiguous()
+            g, o = torch.empty_like(img), torch.empty_like(img)
+            enc = hgi.Encoder(hgi.Crossed, hgi.Linear(Qm(q)), lv, ctx=ctx)
+            dec = hgi.Decoder(hgi.Crossed, ctx=ctx)
+            single[name] = {"encode_us_per_call": per_call_us(lambda s: enc.encode_device(img, grids_out=g, stream=s.cuda_stream)),
+                            "decode_us_per_call": per_call_us(lambda s: dec.decode_device(lv, g, images_out=o, stream=s.cuda_stream))}
+        out["single_plane"] = dict(single, method="200 back-to-back hgi_*_dev calls replayed from one CUDA graph, best of 5")
+    # ---- configs[3]: 16384 x 16384, level 8, Medium
+    n16, lv = 16384, 8
+    enc = hgi.Encoder(hgi.Crossed, hgi.Linear(Qm.Medium), lv, ctx=ctx)
+    dec = hgi.Decoder(hgi.Crossed, ctx=ctx)
+    xx = torch.arange(n16, device=dev, dtype=torch.int32)[None, :]
+    st = torch.cuda.Stream(dev)                       # a real stream: the launch chain is replayed from a graph
+    if rank == 0:
+        yy = torch.arange(n16, device=dev, dtype=torch.int32)[:, None]
+        img = ((xx * yy) & 255).to(torch.uint8).contiguous()
+        g, o = torch.empty_like(img), torch.empty_like(img)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(st):
+            te = time_events(lambda: enc.encode_device(img, grids_out=g, stream=st.cuda_stream), st, 20) * 1e3
+            td = time_events(lambda: dec.decode_device(lv, g, images_out=o, stream=st.cuda_stream), st, 20) * 1e3
+        err = int((o[::64].to(torch.int16) - img[::64].to(torch.int16)).abs().max().item())
+        assert err <= 20 and torch.equal(o[::256, ::256], img[::256, ::256])
+        px = float(n16) * n16
+        out["c4_16384_L8_medium_1gpu"] = {"encode_us": te, "decode_us": td,
+                                          "encode_frac_of_peak": 2 * px / (te * 1e-6) / 1e9 / peak,
+                                          "decode_frac_of_peak": 2 * px / (td * 1e-6) / 1e9 / peak,
+                                          "graph_launches": ctx.graph_launches}
+        del img, g, o
+    if world > 1:
+        # row bands: rank r owns band r (heights multiples of 256, 257 overlap rows), no exchange
+        bands = hgi.sharding.plan_bands(n16, lv, world)
+        t_ms = -1.0
+        if rank < len(bands):
+            bd = bands[rank]
+            yy = torch.arange(bd.y0, bd.in_y1, device=dev, dtype=torch.int32)[:, None]
+            bimg = ((xx * yy) & 255).to(torch.uint8).contiguous()
+            bg, bo = torch.empty_like(bimg), torch.empty_like(bimg)
+
+            def band_step():
+                enc.encode_device(bimg, grids_out=bg, stream=st.cuda_stream)
+                dec.decode_device(lv, bg, images_out=bo, stream=st.cuda_stream)
+            torch.cuda.synchronize()
+            barrier()
+            with torch.cuda.stream(st):
+                t_ms = time_events(band_step, st, 50, warm=5)
+        else:
+            barrier()
+        t = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            one = out["c4_16384_L8_medium_1gpu"]
+            out["c4_row_bands"] = {"ranks": world, "bands": len(bands), "encode_plus_decode_us": float(t.item()) * 1e3,
+                                   "vs_1gpu": (one["encode_us"] + one["decode_us"]) / (float(t.item()) * 1e3),
+                                   "rows_in_per_rank": bands[0].rows_in, "rows_out_per_rank": bands[0].rows_out,
+                                   "timing": "max over ranks, CUDA events over 50 encode+decode pairs per rank"}
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import rustyhgi_b200 as hgi
@@ -247,7 +395,8 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("HGI_BENCH_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL_DEBUG is whatever the launcher set; only its log file defaults to stderr so that stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
@@ -322,6 +471,37 @@ def run_ours(args, rank, world, local_rank):
     # sanity: the timed outputs are real (last pass was Medium): bounded error, seeds raw
     err = int((back[:8].to(torch.int16) - frames[:8].to(torch.int16)).abs().max().item())
     assert err <= 20 and torch.equal(back[:8, ::16, ::16], frames[:8, ::16, ::16]), "bench output failed sanity"
+
+    # ---- strong scaling of the workload as BASELINE configs[4] words it: 4096 frames in total, 4096 / N per rank ----
+    strong = None
+    if world > 1 and not args.no_extra:
+        share = max(1, frames_n // world)
+        fs, gs, bs = frames[:share], grids[:share], back[:share]
+
+        def strong_step():
+            for enc in encs:
+                enc.encode_device(fs, grids_out=gs)
+                dec.decode_device(LEVELS, gs, images_out=bs)
+        barrier()
+        ms = time_events(strong_step, stream, args.steps)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong = {"frames_total": share * world, "frames_per_gpu": share, "ms_per_step": float(t.item()),
+                  "value": len(QLEVELS) * share * world * W * H / (float(t.item()) * 1e-3) / 1e6, "unit": UNIT,
+                  "note": "the same step over 4096 / N frames per rank (BASELINE configs[4] as written); max over ranks"}
+
+    # ---- full parity of sampled frames against the oracle (rank 0; outside every timed region) ----
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        parity = oracle_parity(frames, encs, dec, ctx)
+        assert parity["mismatches"] == 0, f"bench outputs differ from the oracle: {parity}"
+
+    extra = None
+    if not args.no_extra:
+        encs[1].encode_device(frames, grids_out=grids)             # Medium grids for the histogram block
+        extra = extra_block(hgi, ctx, dev, rank, world, dist, measured_peak()[0], grids, barrier)
+        if strong:
+            extra["strong_scaling"] = strong
 
     # ---- e2e: host-pointer C-ABI calls, pinned host memory, copies inside the timed region ----
     e2e = None
@@ -398,7 +578,7 @@ def run_ours(args, rank, world, local_rank):
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(frames_n, world),
                 "roofline": roofline, "cpu_baseline": None if args.no_cpu else cpu_baseline(), "e2e": e2e,
-                "gpu_launches": int(launches), "clocks": clocks}
+                "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "extra": extra}
         print(json.dumps(line), flush=True)
     ctx.close()
     if dist:
@@ -416,6 +596,7 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=0, help="frames in the pinned e2e buffers (default 1024)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra block (single planes, config 4, histogram, strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -227,8 +227,16 @@ cudaError_t launch_histogram(const uint8_t* data, uint32_t w, uint32_t h, uint32
     if (e != cudaSuccess || n_per_image == 0) return e;
     // Zeroing and reducing the 32 KB of counters costs a block about as much as counting 32 KB of data: give every
     // block 256 KiB when the job is large, and not less than 32 KiB (a single small plane still spreads over the chip)
-    static const cudaError_t attr = cudaFuncSetAttribute(hgi_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem);
-    if (attr != cudaSuccess) return attr;
+    {   // function attributes are per device: opt in to 64 KB of dynamic shared memory once on each
+        static bool done[64] = {};
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return cudaGetLastError();
+        if (dev < 0 || dev >= 64 || !done[dev]) {
+            e = cudaFuncSetAttribute(hgi_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) done[dev] = true;
+        }
+    }
     const uint64_t total = n_per_image * n_images;
     const uint64_t per_block = total >= (512ull << 20) ? (256u << 10) : (total >= (32ull << 20) ? (64u << 10) : (32u << 10));
     uint64_t bpi = (n_per_image + per_block - 1) / per_block;
