@@ -124,6 +124,13 @@ extern "C" {
     pub fn hgi_archive_serialize_huffman(m: *const hgi_metadata_t, grid: *const u8, grid_len: usize, grid_width: u64,
                                          hist: *const u32, n_blocks: usize, block_bytes: usize, out: *mut u8,
                                          out_capacity: usize, out_len: *mut usize) -> c_int;
+    pub fn hgi_rle_histogram_u8(ctx: *mut hgi_ctx_t, grid: *const u8, n: usize, block_bytes: usize, n_blocks: usize,
+                                hist_out: *mut u32) -> c_int;
+    pub fn hgi_rle_histogram_dev(ctx: *mut hgi_ctx_t, d_grid: *const u8, n: usize, block_bytes: usize, n_blocks: usize,
+                                 d_hist_out: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn hgi_archive_serialize_rle(m: *const hgi_metadata_t, grid: *const u8, grid_len: usize, grid_width: u64,
+                                     hist: *const u32, n_blocks: usize, block_bytes: usize, out: *mut u8,
+                                     out_capacity: usize, out_len: *mut usize) -> c_int;
     pub fn hgi_archive_read_header(data: *const u8, len: usize, m: *mut hgi_metadata_t) -> c_int;
     pub fn hgi_archive_read_grid(data: *const u8, len: usize, grid_out: *mut u8, grid_capacity: usize,
                                  grid_len_out: *mut usize, grid_width_out: *mut u64) -> c_int;

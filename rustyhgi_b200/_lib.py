@@ -81,6 +81,9 @@ PROTOTYPES = {
     "hgi_archive_serialize": (_int, [_pm, _vp, _sz, _u64, _vp, _sz, ctypes.POINTER(_sz)]),
     "hgi_archive_huffman_bound": (_sz, [_sz, _sz]),
     "hgi_archive_serialize_huffman": (_int, [_pm, _vp, _sz, _u64, _vp, _sz, _sz, _vp, _sz, ctypes.POINTER(_sz)]),
+    "hgi_rle_histogram_u8": (_int, [_vp, _vp, _sz, _sz, _sz, _vp]),
+    "hgi_rle_histogram_dev": (_int, [_vp, _vp, _sz, _sz, _sz, _vp, _vp]),
+    "hgi_archive_serialize_rle": (_int, [_pm, _vp, _sz, _u64, _vp, _sz, _sz, _vp, _sz, ctypes.POINTER(_sz)]),
     "hgi_archive_read_header": (_int, [_vp, _sz, _pm]),
     "hgi_archive_read_grid": (_int, [_vp, _sz, _vp, _sz, ctypes.POINTER(_sz), ctypes.POINTER(_u64)]),
 }

@@ -491,6 +491,9 @@ class Archive:
 
     def serialize_to_writer(self, w, entropy="deflate", hist=None, block_rows=None, ctx=None):
         """entropy="deflate": zlib level-9 raw DEFLATE (the stand-in for flate2's Compression::best()).
+        entropy="rle": literals + distance-1 matches, token tables from the GPU (hgi_rle_histogram_u8 unless `hist`
+        carries the (n_blocks, 288) tables), host bit-packing (hgi_archive_serialize_rle): zlib-9 size on residual
+        planes at ~1/100 of its time; blocks are `block_rows` rows rounded to 512-byte multiples.
         entropy="huffman": GPU-built frequency tables + host bit-packing (hgi_archive_serialize_huffman);
         `hist` may carry the (n_blocks, 256) tables already produced by encode, else they are computed on the
         GPU here, one table per `block_rows` grid rows (default: one table for the whole grid)."""
@@ -518,8 +521,25 @@ class Archive:
                                                  hist.ctypes.data, n_blocks, block, out.ctypes.data, cap, ctypes.byref(n))
             if rc:
                 raise HgiError(rc, "hgi_archive_serialize_huffman")
+        elif entropy == "rle":
+            seg = 512
+            block = buf.size if not block_rows else -(-int(block_rows) * self.grid.width // seg) * seg
+            block = max(1, min(block, max(buf.size, 1)))
+            n_blocks = max(1, -(-buf.size // block))
+            if hist is None:
+                hist = np.zeros((n_blocks, 288), np.uint32)
+                c = ctx or Context.default()
+                c.check(L.hgi_rle_histogram_u8(c._h, buf.ctypes.data if buf.size else None, buf.size, block, n_blocks,
+                                               hist.ctypes.data), "hgi_rle_histogram_u8")
+            hist = np.ascontiguousarray(np.asarray(hist).reshape(n_blocks, 288), dtype=np.uint32)
+            cap = L.hgi_archive_huffman_bound(buf.size, n_blocks)
+            out = np.empty(cap, np.uint8)
+            rc = L.hgi_archive_serialize_rle(ctypes.byref(m), buf.ctypes.data, buf.size, self.grid.width,
+                                             hist.ctypes.data, n_blocks, block, out.ctypes.data, cap, ctypes.byref(n))
+            if rc:
+                raise HgiError(rc, "hgi_archive_serialize_rle")
         else:
-            raise ValueError("entropy must be 'deflate' or 'huffman'")
+            raise ValueError("entropy must be 'deflate', 'rle' or 'huffman'")
         w.write(out[:n.value].tobytes())
 
     @classmethod

@@ -38,6 +38,10 @@ def _level(text):
 def _encoding_options(p):
     p.add_argument("-l", "--level", type=int, default=4)                      # src/options.rs:55-56
     p.add_argument("-q", "--quantizator", type=_level, default="medium")      # src/options.rs:58-64
+    # not in the reference: which DEFLATE encoder writes the payload.  "rle" = GPU-built token tables + host bit
+    # packing (zlib-9 size on residual planes, ~100x faster); "deflate" = zlib level 9, the closest stand-in for
+    # flate2's Compression::best().  Every choice is a raw DEFLATE stream the reference reads.
+    p.add_argument("--entropy", choices=("rle", "deflate", "huffman"), default="rle")
 
 
 def build_parser():
@@ -63,7 +67,7 @@ def encode(a):                                            # src/main.rs:41-61
     grid = api.Encoder(api.Crossed, api.Linear(a.quantizator), a.level).encode(image)
     md = api.Metadata(a.quantizator, api.InterpolationType.Crossed, w, h, a.level)
     with open(a.output, "wb") as f:
-        api.Archive(md, grid).serialize_to_writer(f)
+        api.Archive(md, grid).serialize_to_writer(f, entropy=a.entropy)
 
 
 def decode(a):                                            # src/main.rs:63-71
@@ -84,7 +88,7 @@ def test(a, out=None):                                    # src/main.rs:73-120
     after = api.Decoder(api.Crossed).decode((w, h), a.level, grid)
     m = api.error_metrics(before, after)
     buf = io.BytesIO()
-    api.Archive(api.Metadata(a.quantizator, api.InterpolationType.Crossed, w, h, a.level), grid).serialize_to_writer(buf)
+    api.Archive(api.Metadata(a.quantizator, api.InterpolationType.Crossed, w, h, a.level), grid).serialize_to_writer(buf, entropy=a.entropy)
     uncompressed, compressed = w * h, len(buf.getvalue())
     print(f"Uncompressed: {uncompressed // 1024} kb", file=out)               # src/main.rs:108-111
     print(f"Compressed:   {compressed // 1024} kb", file=out)

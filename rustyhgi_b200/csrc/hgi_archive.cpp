@@ -168,6 +168,108 @@ void write_huffman_block(BitWriter& bw, const uint64_t freq[257], const uint8_t*
     bw.put(lit_code[256], lit_len[256]);   // end of block
 }
 
+// ---- run-length DEFLATE: literals + distance-1 matches, tables from the GPU ---------------------------------------
+// The parse (which bytes become literals, which runs become matches) is a pure function of the data and MUST equal
+// the one hgi_rle_hist_kernel counted (hgi_reduce_kernels.cu): 512-byte segments relative to the block start; in a
+// segment every maximal run of a byte b: literal b, then matches of min(258, rest) while rest >= 3, then `rest`
+// literals b.  RFC 1951 3.2.5 length symbols; the only distance is 1 (distance symbol 0, a one-bit code).
+constexpr size_t kRleSeg = HGI_RLE_SEGMENT_BYTES;
+inline uint32_t rle_len_sym(uint32_t len, uint32_t* extra_bits, uint32_t* extra)
+{
+    if (len == 258u) { *extra_bits = 0; *extra = 0; return 285u; }
+    const uint32_t l = len - 3u;
+    uint32_t e = 0;
+    if (l >= 8u) { e = 0; while ((l >> (e + 3)) != 0) ++e; }   // floor(log2(l)) - 2
+    *extra_bits = e;
+    *extra = l & ((1u << e) - 1u);
+    return 257u + 4u * e + (l >> e);
+}
+
+// One dynamic-Huffman block: `pre` literals, the RLE parse of data[0, n), `post` literals; code from freq[286]
+// (the GPU table of this block plus the pre/post bytes and the end-of-block symbol).  Returns false when the table
+// does not cover a symbol the parse needs (i.e. it was not built from this data).
+bool write_rle_block(BitWriter& bw, const uint64_t freq[286], const uint8_t* pre, size_t npre, const uint8_t* data, size_t n,
+                     const uint8_t* post, size_t npost, bool final_block)
+{
+    uint8_t lit_len[286];
+    uint16_t lit_code[286];
+    huffman_lengths(freq, 286, 15, lit_len);
+    canonical_codes(lit_len, 286, lit_code);
+    int hlit = 286;
+    while (hlit > 257 && lit_len[hlit - 1] == 0) --hlit;
+    uint8_t seq[287];
+    std::memcpy(seq, lit_len, (size_t)hlit);
+    seq[hlit] = 1;   // one distance code (distance 1), "encoded using one bit" (RFC 1951 3.2.7)
+    const int nseq = hlit + 1;
+    struct Tok { uint8_t sym, extra_bits; uint16_t extra; };
+    std::vector<Tok> toks;
+    for (int i = 0; i < nseq;) {
+        const uint8_t v = seq[i];
+        int run = 1;
+        while (i + run < nseq && seq[i + run] == v) ++run;
+        int left = run;
+        if (v == 0) {
+            while (left >= 11) { const int r = left > 138 ? 138 : left; toks.push_back({18, 7, (uint16_t)(r - 11)}); left -= r; }
+            if (left >= 3) { toks.push_back({17, 3, (uint16_t)(left - 3)}); left = 0; }
+            while (left-- > 0) toks.push_back({0, 0, 0});
+        } else {
+            toks.push_back({v, 0, 0});
+            --left;
+            while (left >= 3) { const int r = left > 6 ? 6 : left; toks.push_back({16, 2, (uint16_t)(r - 3)}); left -= r; }
+            while (left-- > 0) toks.push_back({v, 0, 0});
+        }
+        i += run;
+    }
+    uint64_t cl_freq[19] = {0};
+    for (const Tok& t : toks) cl_freq[t.sym]++;
+    uint8_t cl_len[19];
+    uint16_t cl_code[19];
+    huffman_lengths(cl_freq, 19, 7, cl_len);
+    canonical_codes(cl_len, 19, cl_code);
+    static const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    int hclen = 19;
+    while (hclen > 4 && cl_len[order[hclen - 1]] == 0) --hclen;
+    bw.put(final_block ? 1u : 0u, 1);   // BFINAL
+    bw.put(2u, 2);                      // BTYPE = 10 (dynamic Huffman)
+    bw.put((uint32_t)(hlit - 257), 5);  // HLIT
+    bw.put(1 - 1, 5);                   // HDIST
+    bw.put((uint32_t)(hclen - 4), 4);   // HCLEN
+    for (int i = 0; i < hclen; ++i) bw.put(cl_len[order[i]], 3);
+    for (const Tok& t : toks) {
+        bw.put(cl_code[t.sym], cl_len[t.sym]);
+        if (t.extra_bits) bw.put(t.extra, t.extra_bits);
+    }
+    bool ok = true;
+    auto lit = [&](uint32_t b) { ok &= lit_len[b] != 0; bw.put(lit_code[b], lit_len[b]); };
+    for (size_t i = 0; i < npre; ++i) lit(pre[i]);
+    for (size_t s0 = 0; s0 < n; s0 += kRleSeg) {
+        const size_t s1 = s0 + kRleSeg < n ? s0 + kRleSeg : n;
+        size_t i = s0;
+        while (i < s1) {
+            const uint8_t b = data[i];
+            size_t j = i + 1;
+            while (j < s1 && data[j] == b) ++j;
+            lit(b);
+            uint32_t rem = (uint32_t)(j - i - 1);
+            while (rem >= 3u) {
+                const uint32_t m = rem < 258u ? rem : 258u;
+                uint32_t eb, ev;
+                const uint32_t sym = rle_len_sym(m, &eb, &ev);
+                ok &= lit_len[sym] != 0;
+                bw.put(lit_code[sym], lit_len[sym]);
+                if (eb) bw.put(ev, (int)eb);
+                bw.put(0u, 1);          // distance symbol 0 (distance 1), the one-bit code
+                rem -= m;
+            }
+            for (; rem; --rem) lit(b);
+            i = j;
+        }
+    }
+    for (size_t i = 0; i < npost; ++i) lit(post[i]);
+    bw.put(lit_code[256], lit_len[256]);   // end of block
+    return ok;
+}
+
 extern "C" {
 
 size_t hgi_archive_bound(size_t n)
@@ -271,6 +373,44 @@ int hgi_archive_serialize_huffman(const hgi_metadata_t* m, const uint8_t* grid, 
     return HGI_OK;
 }
 
+int hgi_archive_serialize_rle(const hgi_metadata_t* m, const uint8_t* grid, size_t grid_len, uint64_t grid_width,
+                              const uint32_t* hist, size_t n_blocks, size_t block_bytes, uint8_t* out,
+                              size_t out_capacity, size_t* out_len)
+{
+    if (!m || !out || !out_len || !hist || n_blocks == 0 || (grid_len && !grid)) return HGI_ERR_INVALID_ARG;
+    if (m->quantization_level > 3 || m->interpolation > 2) return HGI_ERR_INVALID_ARG;
+    if (n_blocks > 1 && (block_bytes == 0 || block_bytes % kRleSeg != 0 || (n_blocks - 1) * block_bytes >= grid_len ||
+                         n_blocks * block_bytes < grid_len))
+        return HGI_ERR_INVALID_ARG;
+    if (out_capacity < HGI_ARCHIVE_HEADER_BYTES) return HGI_ERR_BUFFER_TOO_SMALL;
+    put_u32(out + 0, HGI_ARCHIVE_MAGIC);
+    put_u32(out + 4, m->quantization_level);
+    put_u32(out + 8, m->interpolation);
+    put_u32(out + 12, m->width);
+    put_u32(out + 16, m->height);
+    put_u64(out + 20, m->scale_level);
+    uint8_t lenb[8], widthb[8];
+    put_u64(lenb, (uint64_t)grid_len);       // bincode(Grid): Vec<u8> length prefix, bytes, then `width: usize`
+    put_u64(widthb, grid_width);
+    BitWriter bw(out + HGI_ARCHIVE_HEADER_BYTES, out_capacity - HGI_ARCHIVE_HEADER_BYTES);
+    for (size_t b = 0; b < n_blocks; ++b) {
+        const size_t lo = n_blocks == 1 ? 0 : b * block_bytes;
+        const size_t hi = (n_blocks == 1 || b + 1 == n_blocks) ? grid_len : lo + block_bytes;
+        uint64_t freq[286];
+        for (int i = 0; i < 286; ++i) freq[i] = hist[b * HGI_RLE_TABLE_SYMBOLS + i];
+        freq[256] = 1;                                       // end-of-block
+        const bool first = (b == 0), last = (b + 1 == n_blocks);
+        if (first) for (int i = 0; i < 8; ++i) freq[lenb[i]]++;
+        if (last) for (int i = 0; i < 8; ++i) freq[widthb[i]]++;
+        if (!write_rle_block(bw, freq, lenb, first ? 8 : 0, grid + lo, hi - lo, widthb, last ? 8 : 0, last))
+            return HGI_ERR_INVALID_ARG;                      // the table was not built from this block
+    }
+    bw.finish();
+    if (bw.overflow()) return HGI_ERR_BUFFER_TOO_SMALL;
+    *out_len = (size_t)(bw.pos() - out);
+    return HGI_OK;
+}
+
 int hgi_archive_read_header(const uint8_t* data, size_t len, hgi_metadata_t* m)
 {
     if (!data || !m) return HGI_ERR_INVALID_ARG;
@@ -327,9 +467,14 @@ int hgi_archive_read_grid(const uint8_t* data, size_t len, uint8_t* grid_out, si
     if (rc == HGI_OK) {
         glen = get_u64(b8);
         *grid_len_out = (size_t)glen;
-        if (!grid_out || glen > grid_capacity) rc = HGI_ERR_BUFFER_TOO_SMALL;
+        // a deflate stream expands at most 1032x: a length prefix beyond that (or beyond width * height of the
+        // header when that is known) cannot be honest -- refuse before anybody allocates for it
+        const uint64_t by_ratio = (uint64_t)(len - HGI_ARCHIVE_HEADER_BYTES) * 1032u + 1032u;
+        const uint64_t by_dims = (uint64_t)m.width * m.height;
+        if (glen > by_ratio || (by_dims != 0 && glen > by_dims)) rc = HGI_ERR_TRUNCATED;
+        else if (glen > 0 && (!grid_out || glen > grid_capacity)) rc = HGI_ERR_BUFFER_TOO_SMALL;
     }
-    if (rc == HGI_OK) rc = pull(grid_out, (size_t)glen);
+    if (rc == HGI_OK && glen) rc = pull(grid_out, (size_t)glen);
     if (rc == HGI_OK) rc = pull(b8, 8);
     if (rc == HGI_OK && grid_width_out) *grid_width_out = get_u64(b8);
     inflateEnd(&zs);

@@ -763,6 +763,52 @@ int hgi_histogram_dev(hgi_ctx_t* ctx, const uint8_t* d_grid, size_t n_per_image,
     return HGI_OK;
 }
 
+int hgi_rle_histogram_dev(hgi_ctx_t* ctx, const uint8_t* d_grid, size_t n, size_t block_bytes, size_t n_blocks,
+                          uint32_t* d_hist_out, void* stream)
+{
+    if (!ctx || !d_hist_out || n_blocks == 0 || n_blocks > 65535) return HGI_ERR_INVALID_ARG;
+    if (n && !d_grid) return HGI_ERR_INVALID_ARG;
+    if (n_blocks == 1) block_bytes = n ? n : 1;
+    if (block_bytes == 0 || block_bytes >= ((size_t)1 << 32) || (n_blocks > 1 && block_bytes % HGI_RLE_SEGMENT_BYTES != 0) ||
+        (n_blocks - 1) * block_bytes > n || n_blocks * block_bytes < n)
+        return HGI_ERR_INVALID_ARG;
+    DeviceGuard g(ctx);
+    if (!g.ok) return HGI_ERR_CUDA;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    HGI_CUDA(ctx, hgi::launch_rle_histogram(d_grid, n, block_bytes, (uint32_t)n_blocks, d_hist_out, st));
+    ctx->launches++;
+    return HGI_OK;
+}
+
+int hgi_rle_histogram_u8(hgi_ctx_t* ctx, const uint8_t* grid, size_t n, size_t block_bytes, size_t n_blocks, uint32_t* hist_out)
+{
+    if (!ctx || !hist_out || n_blocks == 0 || n_blocks > 65535) return HGI_ERR_INVALID_ARG;
+    if (n && !grid) return HGI_ERR_INVALID_ARG;
+    DeviceGuard g(ctx);
+    if (!g.ok) return HGI_ERR_CUDA;
+    Slot& sl = ctx->slots[0];
+    if (!sl.stream) HGI_CUDA(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    int rc = reserve(ctx, sl.in, n ? n : 1);
+    if (rc) return rc;
+    const size_t hwords = n_blocks * HGI_RLE_TABLE_SYMBOLS;
+    if (sl.hist_cap < hwords) {
+        if (sl.hist) HGI_CUDA(ctx, cudaFree(sl.hist));
+        sl.hist = nullptr;
+        sl.hist_cap = 0;
+        HGI_CUDA(ctx, cudaMalloc((void**)&sl.hist, hwords * sizeof(uint32_t)));
+        sl.hist_cap = hwords;
+    }
+    if (n) HGI_CUDA(ctx, cudaMemcpyAsync(sl.in.p, grid, n, cudaMemcpyHostToDevice, sl.stream));
+    rc = hgi_rle_histogram_dev(ctx, sl.in.p, n, block_bytes, n_blocks, sl.hist, sl.stream);
+    if (rc == HGI_OK) {
+        const cudaError_t e = cudaMemcpyAsync(hist_out, sl.hist, hwords * sizeof(uint32_t), cudaMemcpyDeviceToHost, sl.stream);
+        if (e != cudaSuccess) rc = fail(ctx, e);
+    }
+    const cudaError_t es = cudaStreamSynchronize(sl.stream);
+    if (es != cudaSuccess && rc == HGI_OK) rc = fail(ctx, es);
+    return rc;
+}
+
 int hgi_error_metrics_dev(hgi_ctx_t* ctx, const uint8_t* d_before, const uint8_t* d_after, size_t n,
                           uint64_t* d_out, void* stream)
 {

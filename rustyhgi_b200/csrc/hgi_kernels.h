@@ -77,6 +77,10 @@ cudaError_t launch_level(int mode, int interp, const LevelArgs& args, cudaStream
 // image); hist_out[img][256] is overwritten.
 cudaError_t launch_histogram(const uint8_t* data, uint32_t w, uint32_t h, uint32_t pitch, uint32_t n_images,
                              uint32_t* hist_out, cudaStream_t stream);
+// Token frequencies of the run-length DEFLATE parse (286 literal/length symbols, rows of 288) of `n` contiguous bytes cut
+// into blocks of `block_bytes` (the last one may be shorter): hist_out[n_blocks][288], overwritten.
+cudaError_t launch_rle_histogram(const uint8_t* data, size_t n, size_t block_bytes, uint32_t n_blocks, uint32_t* hist_out,
+                                 cudaStream_t stream);
 cudaError_t launch_rgb_to_luma(const uint8_t* rgb, size_t n_pixels, uint8_t* luma, cudaStream_t stream);
 cudaError_t launch_error_metrics(const uint8_t* before, const uint8_t* after, size_t n,
                                  unsigned long long* out2, cudaStream_t stream);

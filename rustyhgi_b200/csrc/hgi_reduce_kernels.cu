@@ -105,6 +105,59 @@ hgi_hist_kernel(const uint8_t* __restrict__ data, uint32_t w, uint32_t h, uint32
     }
 }
 
+// ---- token statistics of the run-length DEFLATE parse (entropy stage of the container) -----------
+// The host writes a residual plane as DEFLATE literals plus distance-1 matches ("repeat the previous byte n times");
+// on residual planes that is as small as zlib level 9.  This kernel builds the frequency table of that parse -- 286
+// literal/length symbols -- so that the host only bit-packs.  The parse is fixed by hgi_rle_parse.h: the bytes of a
+// block are cut into 512-byte segments; inside a segment every maximal run of equal bytes becomes one literal, then
+// matches of min(258, rest) bytes while at least 3 bytes remain, then the last 0..2 bytes as literals.  One thread
+// walks one segment; the counts go through a per-block table in shared memory (few updates per segment when the plane
+// is made of runs, and updates of the same symbol by several lanes merge in the shared-memory increment unit).
+constexpr int kRleSeg = 512;
+constexpr int kRleSyms = 288;
+__device__ __forceinline__ uint32_t rle_len_sym(uint32_t len)   // RFC 1951 3.2.5: length 3..258 -> symbol 257..285
+{
+    if (len == 258u) return 285u;
+    const uint32_t l = len - 3u;
+    const uint32_t e = l < 8u ? 0u : (uint32_t)(29 - __clz((int)l));   // floor(log2(l)) - 2 extra bits
+    return 257u + 4u * e + (l >> e);
+}
+
+__global__ void __launch_bounds__(128)
+hgi_rle_hist_kernel(const uint8_t* __restrict__ data, size_t n, size_t block_bytes, uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t bins[kRleSyms];
+    for (int i = threadIdx.x; i < kRleSyms; i += blockDim.x) bins[i] = 0u;
+    __syncthreads();
+    const size_t blk = blockIdx.y;
+    const size_t blo = blk * block_bytes, bhi = blo + block_bytes < n ? blo + block_bytes : n;
+    const size_t seg = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t lo = blo + seg * kRleSeg;
+    if (lo < bhi) {
+        const size_t hi = lo + kRleSeg < bhi ? lo + kRleSeg : bhi;
+        const uint8_t* p = data + lo;
+        const uint32_t len = (uint32_t)(hi - lo);
+        uint32_t i = 0;
+        while (i < len) {
+            const uint32_t b = p[i];
+            uint32_t j = i + 1;
+            while (j < len && p[j] == b) ++j;
+            atomicAdd(&bins[b], 1u);
+            uint32_t rem = j - i - 1u;
+            while (rem >= 3u) {
+                const uint32_t m = rem < 258u ? rem : 258u;
+                atomicAdd(&bins[rle_len_sym(m)], 1u);
+                rem -= m;
+            }
+            if (rem) atomicAdd(&bins[b], rem);
+            i = j;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kRleSyms; i += blockDim.x)
+        if (bins[i]) atomicAdd(&hist[blk * kRleSyms + i], bins[i]);
+}
+
 // 16 pixels per thread and iteration when both planes are 16-byte aligned: |a - b| per byte, squares summed with a
 // 4-way dot product (exact: 4 * 255^2 per word fits 32 bits, widened to 64 bits per 16 bytes), running byte-wise max.
 __global__ void __launch_bounds__(256)
@@ -245,6 +298,19 @@ cudaError_t launch_histogram(const uint8_t* data, uint32_t w, uint32_t h, uint32
     if (bpi * n_images > 0x7FFFFFFFull) bpi = 0x7FFFFFFFull / n_images;
     if (bpi < 1) return cudaErrorInvalidConfiguration;
     hgi_hist_kernel<<<(uint32_t)(bpi * n_images), HT, kHistSmem, stream>>>(data, w, h, pitch, (uint32_t)bpi, hist_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rle_histogram(const uint8_t* data, size_t n, size_t block_bytes, uint32_t n_blocks, uint32_t* hist_out,
+                                 cudaStream_t stream)
+{
+    if (n_blocks == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(hist_out, 0, (size_t)n_blocks * kRleSyms * sizeof(uint32_t), stream);
+    if (e != cudaSuccess || n == 0) return e;
+    const size_t segs = (block_bytes + kRleSeg - 1) / kRleSeg;
+    const size_t gx = (segs + 127) / 128;
+    if (gx > 0x7FFFFFFFull || n_blocks > 65535u) return cudaErrorInvalidConfiguration;
+    hgi_rle_hist_kernel<<<dim3((uint32_t)gx, n_blocks), 128, 0, stream>>>(data, n, block_bytes, hist_out);
     return cudaGetLastError();
 }
 

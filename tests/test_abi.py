@@ -129,6 +129,67 @@ def test_archive_huffman_entropy_stage(block_rows):
                                                                 block_rows=block_rows)
 
 
+@pytest.mark.parametrize("block_rows", [None, 32])
+def test_archive_rle_entropy_stage(block_rows):
+    """Token tables in (here from the CPU statement of the parse, tests/rle_model.py; the GPU-built ones are checked
+    against it in tests/test_gpu_next_rows.py), literals + distance-1 matches out (hgi_archive_serialize_rle)."""
+    from rle_model import rle_table
+    rng = np.random.default_rng(14)
+    cases = [(64, 48, 3, 2), (300, 200, 4, 3), (1, 1, 0, 0), (97, 13, 4, 0), (40, 1024, 4, 2), (3, 600, 2, 1)]
+    for h, w, levels, q in cases:
+        img = (rng.integers(0, 256, (h, w)) // (1 if q == 0 else 40) * 3).astype(np.uint8)   # long flat runs when quantized
+        grid = oc.encode(img, levels, qlevel=q)
+        buf = grid.reshape(-1)
+        block = buf.size if not block_rows else -(-block_rows * w // 512) * 512
+        hist = rle_table(buf, None if not block_rows else block)
+        md = hgi.Metadata(q, 0, w, h, levels)
+        out = io.BytesIO()
+        hgi.Archive(md, hgi.Grid(grid, w)).serialize_to_writer(out, entropy="rle", hist=hist, block_rows=block_rows)
+        raw = out.getvalue()
+        assert raw[:4].hex() == "55a5adba"
+        payload = zlib.decompress(raw[28:], -15)                  # a conforming inflate (flate2/miniz, zlib) reads it
+        assert payload == buf.size.to_bytes(8, "little") + buf.tobytes() + w.to_bytes(8, "little")
+        assert hgi.Archive.deserialize_from_reader(io.BytesIO(raw)) == hgi.Archive(md, hgi.Grid(grid, w))
+    # runs of every length around the 258 / 512-byte limits, and a table that does not belong to the data
+    data = np.concatenate([np.full(n, 7 + (i & 1), np.uint8) for i, n in enumerate([1, 2, 3, 4, 257, 258, 259, 260, 261, 516, 1100, 5])])
+    out = io.BytesIO()
+    hgi.Archive(hgi.Metadata(0, 0, data.size, 1, 0), hgi.Grid(data, data.size)).serialize_to_writer(out, entropy="rle", hist=rle_table(data))
+    assert zlib.decompress(out.getvalue()[28:], -15)[8:-8] == data.tobytes()
+    bad = rle_table(data)
+    bad[0, 285] = 0                                               # the 258-byte matches lose their code
+    with pytest.raises(hgi.HgiError):
+        hgi.Archive(hgi.Metadata(0, 0, data.size, 1, 0), hgi.Grid(data, data.size)).serialize_to_writer(io.BytesIO(), entropy="rle", hist=bad)
+
+
+def test_archive_rle_is_as_small_as_zlib9_on_a_photograph():
+    """fullhd Medium within 10 % of zlib level 9 (<= 250 KB)."""
+    from conftest import get_plane
+    from rle_model import rle_table
+    grid = oc.encode(get_plane("fullhd"), 4, qlevel=2)
+    payload = grid.size.to_bytes(8, "little") + grid.tobytes() + (1920).to_bytes(8, "little")
+    out = io.BytesIO()
+    hgi.Archive(hgi.Metadata(2, 0, 1920, 1080, 4), hgi.Grid(grid, 1920)).serialize_to_writer(out, entropy="rle", hist=rle_table(grid))
+    raw = out.getvalue()
+    assert zlib.decompress(raw[28:], -15) == payload
+    z9 = zlib.compressobj(9, zlib.DEFLATED, -15)
+    z9 = len(z9.compress(payload) + z9.flush())
+    assert len(raw) <= 250 * 1024 and len(raw) <= 1.10 * z9, (len(raw), z9)
+
+
+def test_archive_reader_refuses_dishonest_length_prefixes():
+    """the u64 bincode length prefix is validated before anybody allocates for it; an empty grid reads back."""
+    co = zlib.compressobj(9, zlib.DEFLATED, -15)
+    lie = co.compress((1 << 39).to_bytes(8, "little") + bytes(32)) + co.flush()
+    head = bytes.fromhex("55a5adba") + (0).to_bytes(4, "little") * 2 + (4).to_bytes(4, "little") * 2 + (1).to_bytes(8, "little")
+    with pytest.raises(hgi.HgiError) as e:
+        hgi.Archive.deserialize_from_reader(io.BytesIO(head + lie))
+    assert e.value.status == -6
+    empty = io.BytesIO()
+    hgi.Archive(hgi.Metadata(0, 0, 0, 0, 1), hgi.Grid(np.zeros(0, np.uint8), 0)).serialize_to_writer(empty)
+    back = hgi.Archive.deserialize_from_reader(io.BytesIO(empty.getvalue()))
+    assert back.grid.buffer.size == 0 and back.metadata.width == 0
+
+
 def test_archive_huffman_skewed_tables_respect_length_limit():
     """Fibonacci-like counts would give code lengths > 15 without the length limit."""
     counts = [1, 1]

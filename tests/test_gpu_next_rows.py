@@ -59,6 +59,43 @@ def test_archive_with_gpu_built_frequency_tables():
     assert sha16(after) == "96db2c544587bccb"
 
 
+def test_rle_tables_from_the_gpu_equal_the_cpu_statement_of_the_parse():
+    """hgi_rle_hist_kernel counts exactly the tokens hgi_archive_serialize_rle will write (tests/rle_model.py states
+    the parse on the CPU); the resulting archive inflates to bincode(Grid) and is within 10 % of zlib level 9."""
+    import torch
+    from rle_model import rle_table
+    ctx = hgi.Context(0)
+    L = hgi.lib()
+    rng = np.random.default_rng(3)
+    planes = [oc.encode(load_plane("fullhd"), 4, qlevel=2), oc.encode(load_plane("lena_tif"), 4, qlevel=0),
+              rng.integers(0, 256, (37, 123)).astype(np.uint8), np.zeros((50, 700), np.uint8),
+              np.repeat(rng.integers(0, 4, (20, 40)).astype(np.uint8), 40, axis=1)]
+    for g in planes:
+        buf = g.reshape(-1)
+        for block in (None, 512 * 7, 512 * 64):
+            nb = 1 if block is None else -(-buf.size // block)
+            want = rle_table(buf, block)
+            got = np.zeros((nb, 288), np.uint32)
+            ctx.check(L.hgi_rle_histogram_u8(ctx._h, buf.ctypes.data, buf.size, block or buf.size, nb, got.ctypes.data), "rle")
+            assert (got == want).all(), (g.shape, block)
+            d = torch.from_numpy(buf).cuda()
+            dh = torch.empty((nb, 288), dtype=torch.int32, device="cuda")
+            ctx.check(L.hgi_rle_histogram_dev(ctx._h, d.data_ptr(), buf.size, block or buf.size, nb, dh.data_ptr(), None), "rle dev")
+            ctx.synchronize()
+            assert (dh.cpu().numpy().astype(np.uint32) == want).all()
+    g = planes[0]
+    arch = hgi.Archive(hgi.Metadata(2, 0, 1920, 1080, 4), hgi.Grid(g, 1920))
+    out = io.BytesIO()
+    arch.serialize_to_writer(out, entropy="rle", ctx=ctx)                 # tables built on the GPU inside
+    raw = out.getvalue()
+    payload = g.size.to_bytes(8, "little") + g.tobytes() + (1920).to_bytes(8, "little")
+    assert zlib.decompress(raw[28:], -15) == payload
+    z9 = zlib.compressobj(9, zlib.DEFLATED, -15)
+    assert len(raw) <= 1.10 * len(z9.compress(payload) + z9.flush()) and len(raw) <= 250 * 1024
+    assert hgi.Archive.deserialize_from_reader(io.BytesIO(raw)) == arch
+    ctx.close()
+
+
 def test_cli_test_subcommand_config1(tmp_path, monkeypatch, capsys):
     """BASELINE config 1: `hgi test res/LENA.TIF` (level 4, Medium) -> `Uncompressed: 64 kb`, `SD: 9.17`."""
     monkeypatch.chdir(tmp_path)
