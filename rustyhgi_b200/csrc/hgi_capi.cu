@@ -35,6 +35,16 @@ size_t chunk_bytes()
     return v;
 }
 
+// HGI_B200_POISON_SCRATCH=<0..255>: fill the device scratch planes with this byte before every launch chain (debug).
+int poison_scratch()
+{
+    static const int v = [] {
+        const char* e = std::getenv("HGI_B200_POISON_SCRATCH");
+        return e && *e ? (int)(std::strtol(e, nullptr, 0) & 255) : -1;
+    }();
+    return v;
+}
+
 struct DevBuf {
     uint8_t* p = nullptr;
     size_t cap = 0;
@@ -289,6 +299,12 @@ int run_tile_path(hgi_ctx* ctx, Scratch& sc, int mode, const uint8_t* src, uint3
         }
         int rc = reserve(ctx, sc, sc.dec_in, max_compact);
         if (rc) return rc;
+    }
+    if (max_compact && poison_scratch() >= 0) {
+        // debug hook (HGI_B200_POISON_SCRATCH=<byte>): the scratch planes start as a known pattern; results must not change
+        for (auto& b : sc.compact)
+            if (b.p) HGI_CUDA(ctx, cudaMemsetAsync(b.p, poison_scratch(), b.cap, st));
+        HGI_CUDA(ctx, cudaMemsetAsync(sc.dec_in.p, poison_scratch(), sc.dec_in.cap, st));
     }
     const uint8_t* c_recon = nullptr;
     const uint8_t* c_q = nullptr;

@@ -162,6 +162,16 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     const bool top = (p.c_recon == nullptr);
     const QuantSwar qc = {p.q_one, p.q_mul, p.q_add, p.q_shift, p.q_scale, p.q_rmask, p.q_qmul, p.q_hK, p.q_hc1, p.q_hS, p.q_hc2};   // filled by the launcher
 
+#ifdef HGI_VAR_POISON_SMEM
+    // Debug variant (tools/build_variant.sh poisonXX -DHGI_VAR_POISON_SMEM=0xXX): the planes start as a known
+    // pattern instead of whatever the previous CTA left.  The kernel is allowed to COMPUTE on unstaged bytes (the
+    // fringe words reach two columns / one row past anything a consumer reads) but no such byte may reach an output:
+    // the parity suite must pass unchanged for every pattern -- the stand-in for `compute-sanitizer --tool
+    // initcheck` on shared memory, which is closed on this pool (profiles/r02_sanitizer.md).
+    for (int i = tid; i < (int)(sizeof(FastSmem) / 4); i += NT)
+        reinterpret_cast<uint32_t*>(&sm)[i] = 0x01010101u * (uint32_t)(HGI_VAR_POISON_SMEM);
+    __syncthreads();
+#endif
     // ---- 1. global loads: this thread's NU 16x2-pixel units (kept in registers for the finest level) ----
     const int sx = tid & 7, ry = tid >> 3;          // 8 column strips x RPB thread rows, NU adjacent row pairs each
     const int nvalid = max(0, min(16, xin - 16 * sx));   // in-image bytes of this thread's chunks (0 or 16 if ALIGNED)
