@@ -62,6 +62,7 @@ extern "C" {
     pub fn hgi_ctx_create(device: c_int, ctx_out: *mut *mut hgi_ctx_t) -> c_int;
     pub fn hgi_ctx_destroy(ctx: *mut hgi_ctx_t);
     pub fn hgi_ctx_set_path(ctx: *mut hgi_ctx_t, path: c_int) -> c_int;
+    pub fn hgi_ctx_set_pipeline(ctx: *mut hgi_ctx_t, chunk_mb: u32, slots: u32) -> c_int;
     pub fn hgi_ctx_synchronize(ctx: *mut hgi_ctx_t) -> c_int;
     pub fn hgi_ctx_last_cuda_error(ctx: *const hgi_ctx_t) -> c_int;
     pub fn hgi_ctx_last_cuda_error_string(ctx: *const hgi_ctx_t) -> *const c_char;

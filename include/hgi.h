@@ -100,6 +100,10 @@ const char *hgi_strerror(int status);
 int hgi_ctx_create(int device, hgi_ctx_t **ctx_out);
 void hgi_ctx_destroy(hgi_ctx_t *ctx);
 int hgi_ctx_set_path(hgi_ctx_t *ctx, int path /* hgi_path_t */);
+/* Host-pointer entry points stream a batch through `slots` (1..4) stream slots in chunks of `chunk_mb` MiB (H2D,
+   kernels and D2H of different chunks overlap).  0 = the default (64 MiB, 3 slots; HGI_B200_CHUNK_MB and
+   HGI_B200_SLOTS in the environment override the default). */
+int hgi_ctx_set_pipeline(hgi_ctx_t *ctx, uint32_t chunk_mb, uint32_t slots);
 int hgi_ctx_synchronize(hgi_ctx_t *ctx);
 /* cudaError_t of the last failing runtime call (0 if none) and its string. */
 int hgi_ctx_last_cuda_error(const hgi_ctx_t *ctx);

@@ -44,6 +44,7 @@ PROTOTYPES = {
     "hgi_ctx_create": (_int, [_int, ctypes.POINTER(_vp)]),
     "hgi_ctx_destroy": (None, [_vp]),
     "hgi_ctx_set_path": (_int, [_vp, _int]),
+    "hgi_ctx_set_pipeline": (_int, [_vp, _u32, _u32]),
     "hgi_ctx_synchronize": (_int, [_vp]),
     "hgi_ctx_last_cuda_error": (_int, [_vp]),
     "hgi_ctx_last_cuda_error_string": (ctypes.c_char_p, [_vp]),

@@ -118,6 +118,8 @@ struct hgi_ctx {
     cudaStream_t stream = nullptr;
     cudaError_t last_err = cudaSuccess;
     uint64_t launches = 0;
+    size_t chunk_bytes = 0;                       // host API pipeline (0: default / environment), see hgi_ctx_set_pipeline
+    int n_slots = 0;
     std::vector<StreamScratch*> caller_scratch;   // device API: one scratch set per caller stream
     std::vector<ChainGraph> chains;               // device API: captured launch chains (see ChainKey)
     uint64_t chain_clock = 0, graph_launches = 0;
@@ -539,11 +541,11 @@ int run_host_chunks(hgi_ctx* ctx, int mode, const uint8_t* in, uint32_t n_images
                     const hgi_params_t* prm, uint8_t* out, uint8_t* recon_out, uint32_t* hist_out, int* used_out)
 {
     const size_t plane = (size_t)w * h;
-    uint32_t per = (uint32_t)(chunk_bytes() / plane);
+    uint32_t per = (uint32_t)((ctx->chunk_bytes ? ctx->chunk_bytes : chunk_bytes()) / plane);
     if (per < 1) per = 1;
     if (per > n_images) per = n_images;
     const uint32_t n_chunks = (n_images + per - 1) / per;
-    const int nslots = slot_count();
+    const int nslots = ctx->n_slots ? ctx->n_slots : slot_count();
     const int used = n_chunks < (uint32_t)nslots ? (int)n_chunks : nslots;
     for (int s = 0; s < used; ++s) {
         Slot& sl = ctx->slots[s];
@@ -680,6 +682,14 @@ int hgi_ctx_set_path(hgi_ctx_t* ctx, int path)
 {
     if (!ctx || path < HGI_PATH_TILE || path > HGI_PATH_TILE_TMA) return HGI_ERR_INVALID_ARG;
     ctx->path = path;
+    return HGI_OK;
+}
+
+int hgi_ctx_set_pipeline(hgi_ctx_t* ctx, uint32_t chunk_mb, uint32_t slots)
+{
+    if (!ctx || chunk_mb > 4096 || slots > (uint32_t)kSlots) return HGI_ERR_INVALID_ARG;
+    ctx->chunk_bytes = (size_t)chunk_mb << 20;
+    ctx->n_slots = (int)slots;
     return HGI_OK;
 }
 
