@@ -68,6 +68,10 @@ extern "C" {
     pub fn hgi_ctx_last_cuda_error_string(ctx: *const hgi_ctx_t) -> *const c_char;
     pub fn hgi_ctx_kernel_launches(ctx: *const hgi_ctx_t) -> u64;
     pub fn hgi_ctx_graph_launches(ctx: *const hgi_ctx_t) -> u64;
+    pub fn hgi_host_alloc(bytes: usize) -> *mut c_void;
+    pub fn hgi_host_free(ptr: *mut c_void);
+    pub fn hgi_host_register(ptr: *mut c_void, bytes: usize) -> c_int;
+    pub fn hgi_host_unregister(ptr: *mut c_void) -> c_int;
     pub fn hgi_quant_table(kind: c_int, level: c_int, table_out: *mut u8, error_out: *mut u8) -> c_int;
     pub fn hgi_encode_u8(ctx: *mut hgi_ctx_t, image: *const u8, width: u32, height: u32, params: *const hgi_params_t,
                          grid_out: *mut u8, recon_out: *mut u8) -> c_int;

@@ -12,9 +12,11 @@
 //   Archive::deserialize_from_reader(r)               hgi::Archive::deserialize_from_reader(is)
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <istream>
 #include <iterator>
 #include <memory>
+#include <mutex>
 #include <ostream>
 #include <stdexcept>
 #include <string>
@@ -85,12 +87,95 @@ private:
     hgi_ctx_t* ctx_ = nullptr;
 };
 
+// Plane storage: page-locked host memory (hgi_host_alloc), so that the copies of the host-pointer entry points are
+// single DMAs instead of driver-staged pageable copies (a 1080p encode call: ~0.1 ms instead of ~0.45 ms).  Freed
+// blocks are kept in a small process-wide cache keyed by size, because pinning is expensive and the reference's usage
+// -- one Grid / GrayImage of the same size per call (benches/bench.rs:54-110) -- recycles the same few blocks.
+// `Bytes(n)` / `resize(n)` leave new bytes uninitialised (every entry point overwrites all of them); `Bytes(n, v)`
+// fills.  Falls back to malloc when pinning fails.
+class PinnedPool {
+public:
+    static void* get(size_t bytes, bool* pinned)
+    {
+        {
+            std::lock_guard<std::mutex> lock(mutex());
+            auto& c = cache();
+            for (size_t i = 0; i < c.size(); ++i)
+                if (c[i].bytes == bytes) {
+                    void* p = c[i].p;
+                    c.erase(c.begin() + (long)i);
+                    *pinned = true;
+                    return p;
+                }
+        }
+        void* p = hgi_host_alloc(bytes);
+        *pinned = p != nullptr;
+        return p ? p : ::operator new(bytes ? bytes : 1);
+    }
+    static void put(void* p, size_t bytes, bool pinned)
+    {
+        if (!p) return;
+        if (!pinned) { ::operator delete(p); return; }
+        {
+            std::lock_guard<std::mutex> lock(mutex());
+            if (cache().size() < 8) { cache().push_back(Block{p, bytes}); return; }
+        }
+        hgi_host_free(p);
+    }
+private:
+    struct Block { void* p; size_t bytes; };
+    struct Cache {
+        std::vector<Block> blocks;
+        ~Cache() { for (const Block& b : blocks) hgi_host_free(b.p); }
+    };
+    static std::vector<Block>& cache() { static Cache c; return c.blocks; }
+    static std::mutex& mutex() { static std::mutex m; return m; }
+};
+
+class Bytes {
+public:
+    Bytes() = default;
+    explicit Bytes(size_t n) { alloc(n); }
+    Bytes(size_t n, uint8_t fill) { alloc(n); std::memset(p_, fill, n); }
+    Bytes(const Bytes& o) { alloc(o.n_); if (o.n_) std::memcpy(p_, o.p_, o.n_); }
+    Bytes(Bytes&& o) noexcept : p_(o.p_), n_(o.n_), pinned_(o.pinned_) { o.p_ = nullptr; o.n_ = 0; }
+    Bytes& operator=(Bytes o) noexcept { swap(o); return *this; }
+    ~Bytes() { PinnedPool::put(p_, n_, pinned_); }
+    void swap(Bytes& o) noexcept { std::swap(p_, o.p_); std::swap(n_, o.n_); std::swap(pinned_, o.pinned_); }
+    void resize(size_t n)   // new bytes are uninitialised
+    {
+        if (n == n_) return;
+        Bytes t(n);
+        if (p_ && n_) std::memcpy(t.p_, p_, n < n_ ? n : n_);
+        swap(t);
+    }
+    size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    uint8_t* data() { return p_; }
+    const uint8_t* data() const { return p_; }
+    uint8_t& operator[](size_t i) { return p_[i]; }
+    uint8_t operator[](size_t i) const { return p_[i]; }
+    uint8_t* begin() { return p_; }
+    uint8_t* end() { return p_ + n_; }
+    const uint8_t* begin() const { return p_; }
+    const uint8_t* end() const { return p_ + n_; }
+    bool operator==(const Bytes& o) const { return n_ == o.n_ && (n_ == 0 || std::memcmp(p_, o.p_, n_) == 0); }
+    bool operator!=(const Bytes& o) const { return !(*this == o); }
+private:
+    void alloc(size_t n) { n_ = n; p_ = n ? static_cast<uint8_t*>(PinnedPool::get(n, &pinned_)) : nullptr; }
+    uint8_t* p_ = nullptr;
+    size_t n_ = 0;
+    bool pinned_ = false;
+};
+
 // `image::GrayImage`: row-major u8, stride == width, zero-filled on construction (image 0.19).
 struct GrayImage {
     uint32_t width = 0, height = 0;
-    std::vector<uint8_t> data;
+    Bytes data;
     GrayImage() = default;
-    GrayImage(uint32_t w, uint32_t h) : width(w), height(h), data((size_t)w * h, 0) {}
+    GrayImage(uint32_t w, uint32_t h) : width(w), height(h), data((size_t)w * h, (uint8_t)0) {}
+    struct Uninitialized {};
+    GrayImage(uint32_t w, uint32_t h, Uninitialized) : width(w), height(h), data((size_t)w * h) {}
     std::pair<uint32_t, uint32_t> dimensions() const { return {width, height}; }
     uint8_t& at(uint32_t x, uint32_t y) { return data[(size_t)y * width + x]; }
     uint8_t at(uint32_t x, uint32_t y) const { return data[(size_t)y * width + x]; }
@@ -98,7 +183,7 @@ struct GrayImage {
 
 // src/grid.rs:1-5
 struct Grid {
-    std::vector<uint8_t> buffer;
+    Bytes buffer;
     size_t width = 0;
     uint8_t get(uint32_t column, uint32_t line) const { return buffer[(size_t)line * width + column]; }
     bool operator==(const Grid& o) const { return width == o.width && buffer == o.buffer; }
@@ -118,7 +203,7 @@ public:
         Grid grid;
         grid.width = input.width;
         grid.buffer.resize(input.data.size());
-        if (reconstruction) *reconstruction = GrayImage(input.width, input.height);
+        if (reconstruction) *reconstruction = GrayImage(input.width, input.height, GrayImage::Uninitialized{});
         const hgi_params_t p{(uint32_t)scale_level_, I::id, Q::kind, (int32_t)quantizator_.level()};
         check(hgi_encode_u8(ctx_->get(), input.data.data(), input.width, input.height, &p, grid.buffer.data(),
                             reconstruction ? reconstruction->data.data() : nullptr), "hgi_encode_u8");
@@ -139,7 +224,7 @@ public:
     // `decode(&mut self, (width, height): (u32, u32), levels: usize, grid: &Grid) -> GrayImage` (src/decoder.rs:18-46)
     GrayImage decode(std::pair<uint32_t, uint32_t> dimensions, size_t levels, const Grid& grid)
     {
-        GrayImage image(dimensions.first, dimensions.second);
+        GrayImage image(dimensions.first, dimensions.second, GrayImage::Uninitialized{});   // every pixel is written below
         if (grid.buffer.size() != image.data.size()) throw Error(HGI_ERR_INVALID_ARG, "Decoder::decode");
         const hgi_params_t p{(uint32_t)levels, I::id, HGI_QUANT_NOOP, 0};
         check(hgi_decode_u8(ctx_->get(), grid.buffer.data(), image.width, image.height, &p, image.data.data()),
@@ -168,6 +253,22 @@ struct Archive {
     Metadata metadata;
     Grid grid;
     bool operator==(const Archive& o) const { return metadata == o.metadata && grid == o.grid; }
+
+    // The same container with the fast entropy stage: literals + distance-1 matches, token tables built on the GPU
+    // (hgi_rle_histogram_u8), bit-packed on the host (hgi_archive_serialize_rle).  Any inflate reads it.
+    void serialize_to_writer_rle(std::ostream& w, const std::shared_ptr<Context>& ctx = Context::shared()) const
+    {
+        const hgi_metadata_t m{(uint32_t)metadata.quantization_level, (uint32_t)metadata.interpolation,
+                               metadata.width, metadata.height, (uint64_t)metadata.scale_level};
+        std::vector<uint32_t> table(HGI_RLE_TABLE_SYMBOLS);
+        const size_t n = grid.buffer.size();
+        check(hgi_rle_histogram_u8(ctx->get(), grid.buffer.data(), n, n ? n : 1, 1, table.data()), "hgi_rle_histogram_u8");
+        std::vector<uint8_t> out(hgi_archive_huffman_bound(n, 1));
+        size_t len = 0;
+        check(hgi_archive_serialize_rle(&m, grid.buffer.data(), n, grid.width, table.data(), 1, n ? n : 1, out.data(), out.size(), &len),
+              "hgi_archive_serialize_rle");
+        w.write(reinterpret_cast<const char*>(out.data()), (std::streamsize)len);
+    }
 
     void serialize_to_writer(std::ostream& w) const
     {

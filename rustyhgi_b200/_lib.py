@@ -50,6 +50,10 @@ PROTOTYPES = {
     "hgi_ctx_last_cuda_error_string": (ctypes.c_char_p, [_vp]),
     "hgi_ctx_kernel_launches": (_u64, [_vp]),
     "hgi_ctx_graph_launches": (_u64, [_vp]),
+    "hgi_host_alloc": (_vp, [_sz]),
+    "hgi_host_free": (None, [_vp]),
+    "hgi_host_register": (_int, [_vp, _sz]),
+    "hgi_host_unregister": (_int, [_vp]),
     "hgi_quant_table": (_int, [_int, _int, _vp, _vp]),
     "hgi_encode_u8": (_int, [_vp, _vp, _u32, _u32, _pp, _vp, _vp]),
     "hgi_decode_u8": (_int, [_vp, _vp, _u32, _u32, _pp, _vp]),

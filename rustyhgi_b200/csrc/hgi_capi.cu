@@ -712,6 +712,41 @@ const char* hgi_ctx_last_cuda_error_string(const hgi_ctx_t* ctx)
 uint64_t hgi_ctx_kernel_launches(const hgi_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
 uint64_t hgi_ctx_graph_launches(const hgi_ctx_t* ctx) { return ctx ? ctx->graph_launches : 0; }
 
+void* hgi_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void hgi_host_free(void* ptr)
+{
+    if (ptr && cudaFreeHost(ptr) != cudaSuccess) (void)cudaGetLastError();
+}
+
+int hgi_host_register(void* ptr, size_t bytes)
+{
+    if (!ptr || !bytes) return HGI_ERR_INVALID_ARG;
+    if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return HGI_ERR_CUDA;
+    }
+    return HGI_OK;
+}
+
+int hgi_host_unregister(void* ptr)
+{
+    if (!ptr) return HGI_ERR_INVALID_ARG;
+    if (cudaHostUnregister(ptr) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return HGI_ERR_CUDA;
+    }
+    return HGI_OK;
+}
+
 int hgi_quant_table(int quant_kind, int quant_level, uint8_t table_out[256], uint8_t* error_out)
 {
     if (!table_out) return HGI_ERR_INVALID_ARG;

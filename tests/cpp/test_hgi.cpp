@@ -54,6 +54,9 @@ static void serde()                                                 // src/lib.r
     archive.serialize_to_writer(buffer);
     const Archive back = Archive::deserialize_from_reader(buffer);
     ASSERT(back == archive);
+    std::stringstream rle;                                          // the fast entropy stage writes the same container
+    archive.serialize_to_writer_rle(rle);
+    ASSERT(Archive::deserialize_from_reader(rle) == archive);
     std::stringstream bad("\x01\x02\x03\x04 not an archive at all ........");
     bool threw = false;
     try { Archive::deserialize_from_reader(bad); } catch (const Error& e) { threw = e.status() == HGI_ERR_BAD_MAGIC; }

@@ -76,6 +76,15 @@ int main()
         const Archive archive{metadata, grid};
         bench("serialization", 0, [&] { std::ostringstream os; archive.serialize_to_writer(os); }, 5);
     }
+    {   // the same container through the run-length entropy stage (GPU-built token tables, host bit-packing)
+        const Archive archive{metadata, grid};
+        bench("serialization (rle)", 0, [&] { std::ostringstream os; archive.serialize_to_writer_rle(os); }, 5);
+        bench("compression (rle)", 0, [&] {
+            const Archive a2{metadata, encoder.encode(image)};
+            std::ostringstream os;
+            a2.serialize_to_writer_rle(os);
+        }, 5);
+    }
     {   // "compression" = encode + serialise (:129-151)
         bench("compression", 0, [&] {
             const Archive archive{metadata, encoder.encode(image)};
