@@ -337,6 +337,7 @@ int run_tile_path(hgi_ctx* ctx, Scratch& sc, int mode, const uint8_t* src, uint3
             a.recon_out = recon_out;
             a.vec_ok = (pitch % 16 == 0) && aligned16(src) && (grid_out == nullptr || aligned16(grid_out)) &&
                        (recon_out == nullptr || aligned16(recon_out));
+            if (a.vec_ok && (w % 16 != 0)) a.vec_ok = 2;   // padded rows: the last chunk of a row holds padding
         } else {
             const int set = (int)(i & 1) * 2;
             a.s_recon = sc.compact[set].p;

@@ -35,7 +35,7 @@ struct PassArgs {
     uint32_t fast_tx, fast_itx, fast_ity;   // fast tile kernel, split launch: tiles per row, interior tile columns / rows
     uint32_t n_images;
     uint32_t quant_error;    // 0 => identity quantizer
-    uint32_t vec_ok;         // D==1 and rows are 16-byte aligned => 128-bit global accesses
+    uint32_t vec_ok;         // rows and bases are 16-byte aligned => 128-bit global accesses (1: rows are whole chunks, 2: padded rows)
     // SWAR quantizer constants (quant_swar() of hgi_tile_swar.cuh, evaluated on the host per launch)
     uint32_t q_one, q_mul, q_add, q_shift, q_scale, q_rmask, q_qmul;
     uint32_t q_hK, q_hc1, q_hS, q_hc2;   // fp16x2 form

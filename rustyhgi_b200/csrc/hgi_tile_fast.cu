@@ -65,15 +65,17 @@ namespace {
 // 4-byte aligned, else five aligned loads funnel-shifted into place (`may_overread` says the 1..3 bytes after the
 // chunk are still inside the plane batch) / aligned middle words plus byte head and tail for stores; ragged chunks
 // at the right image edge use byte accesses.  Bytes beyond the image read as 0 and are never written.
+// `ragged` (CTA-uniform, from the launch arguments): rows are padded and the width is not a multiple of 16, so an
+// ALIGNED chunk may hold padding; with whole-chunk rows the masking code is skipped by a uniform branch.
 template <bool ALIGNED>
-__device__ __forceinline__ uint4 load_chunk(const uint8_t* __restrict__ ptr, int nvalid, bool may_overread)
+__device__ __forceinline__ uint4 load_chunk(const uint8_t* __restrict__ ptr, int nvalid, bool may_overread, bool ragged)
 {
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (nvalid <= 0) return v;
     if (ALIGNED) {
         // padded rows: the chunk is in memory as a whole, bytes beyond the image are the caller's padding -> read as 0
         uint4 a = __ldg(reinterpret_cast<const uint4*>(ptr));
-        if (nvalid < 16) {
+        if (ragged && nvalid < 16) {
             const uint32_t nb = (uint32_t)nvalid;
             a.x &= nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
             a.y &= nb >= 8 ? 0xFFFFFFFFu : (nb <= 4 ? 0u : ((1u << (8 * (nb - 4))) - 1u));
@@ -160,6 +162,7 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     const size_t pitch = (size_t)p.pitch;
     const uint8_t* __restrict__ tile = p.src + tile_off;
     const bool top = (p.c_recon == nullptr);
+    const bool ragged = EDGE && ALIGNED && p.vec_ok == 2u;   // padded rows whose width is not a multiple of 16
     const QuantSwar qc = {p.q_one, p.q_mul, p.q_add, p.q_shift, p.q_scale, p.q_rmask, p.q_qmul, p.q_hK, p.q_hc1, p.q_hS, p.q_hc2};   // filled by the launcher
 
 #ifdef HGI_VAR_POISON_SMEM
@@ -185,8 +188,8 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
         // a complete chunk may be over-read by <= 3 bytes unless it ends the very last row of the batch
         const bool last0 = EDGE && (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 1 >= p.h) && (X0 + 16u * sx + 16u >= p.pitch);
         const bool last1 = EDGE && (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 2 >= p.h) && (X0 + 16u * sx + 16u >= p.pitch);
-        ev[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * u) * p.pitch, y < yin ? nvalid : 0, !last0);
-        od[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * u + 1) * p.pitch, y + 1 < yin ? nvalid : 0, !last1);
+        ev[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * u) * p.pitch, y < yin ? nvalid : 0, !last0, ragged);
+        od[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * u + 1) * p.pitch, y + 1 < yin ? nvalid : 0, !last1, ragged);
     }
 
     // halo chunks (right of / below the tile) feed only the coarse planes; the upper half of the CTA
@@ -202,7 +205,7 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     const bool halo = NLEV > 1 && hj >= 0 && hj < NHALO;
     uint4 hv = make_uint4(0u, 0u, 0u, 0u);
     if (halo && hy < yin) {
-        hv = load_chunk<ALIGNED>(tile + (uint32_t)hy * p.pitch + (uint32_t)(16 * hc), min(16, xin - 16 * hc), false);
+        hv = load_chunk<ALIGNED>(tile + (uint32_t)hy * p.pitch + (uint32_t)(16 * hc), min(16, xin - 16 * hc), false, ragged);
     }
 
     // ---- 2. stage the dense coarse planes + the coarse lattice of this pass ---------------------
@@ -487,7 +490,7 @@ cudaError_t launch_fast_t(const PassArgs& args_in, cudaStream_t stream)
         v.grid_out = a.s_q;
         v.recon_out = a.s_recon;
         v.d_log2 = 0;
-        v.vec_ok = 1;         // dpitch is a 16-byte multiple and the scratch planes are cudaMalloc'ed
+        v.vec_ok = (a.wD & 15u) ? 2u : 1u;   // dpitch is a 16-byte multiple and the scratch planes are cudaMalloc'ed
         a = v;
     }
     if (a.vec_ok) {
