@@ -10,23 +10,26 @@ namespace hgi {
 
 namespace {
 
-constexpr int HT = 256;
+#ifndef HGI_HIST_THREADS
+#define HGI_HIST_THREADS 1024
+#endif
+#ifndef HGI_HIST_BLOCK_KB
+#define HGI_HIST_BLOCK_KB 1024
+#endif
+constexpr int HT = HGI_HIST_THREADS;
 
 // Residual histogram.  Each block owns a slice of one image (a contiguous byte range of a packed plane, a range of
 // rows of a pitched one) and counts it into PRIVATE bins in shared memory: one column of 256 counters per lane,
 // cell(bin, lane) at byte offset bin * 256 + lane * 4, so the 32 lanes of a warp always hit 32 different banks --
 // every update is one conflict-free wavefront whatever the symbol statistics (a residual plane is mostly one symbol,
-// the worst case for bins shared inside a warp; partially merged or partially predicated updates are 2.5x slower on
-// this machine than full conflict-free ones, tools/ubench_hist.cu).  The 256-byte bin stride (half of it padding,
-// 64 KB per block) makes the cell's offset ONE byte permute of the data word and the lane constant, [lane*4, byte k,
-// 0, 0], used directly as the address of the update: two instructions per byte (PRMT + the update, 1.2 clocks per
-// 32 bytes per SM against 2.6 with the 128-byte stride that needs a multiply-add), which moves the kernel from the
-// shared-memory update rate to the HBM roofline.  The eight warps of a block share the columns; the updates are
-// fire-and-forget increments of the shared-memory unit (no value returns, no retry loop).  The unit slows down when
-// many lanes of one instruction fall into the same 128-byte row (24 of 32 lanes: 3.8 clocks instead of 2.6), which is
-// exactly what a mostly-zero residual plane does to bin 0; so lane l keeps bin b in row b ^ (8 * l): equal symbols
-// of different lanes land in 32 different rows, at the price of one XOR per four bytes.  At the end the block sums
-// each bin over its 32 lanes with warp shuffles and issues one global RED per non-empty bin.
+// the worst case for bins shared inside a warp: partially merged updates are 2.5x slower on this machine than
+// conflict-free ones, and MATCH.ANY costs 67 clocks per warp, tools/ubench_hist.cu).  The 256-byte bin stride (half
+// of it padding, 64 KB per block) makes the cell's offset ONE byte permute of the data word and the lane constant,
+// [lane*4, byte k, 0, 0]: PRMT + base add + update per byte.  The warps of a block share the columns; the updates are
+// fire-and-forget increments of the shared-memory unit (no value returns, no retry loop).  What decides the speed is
+// how many warps keep that unit and the loads busy: 1024-thread blocks (two per SM, all 64 warp slots) with 1 MB of
+// data each run at 5.8 TB/s, 256-thread blocks with 256 KB at 3.8 TB/s (A/B in profiles/r02_histogram.md).  At the
+// end the block sums each bin over its 32 lanes with warp shuffles and issues one global RED per non-empty bin.
 constexpr int kHistBinStride = 256;                         // bytes between bins
 constexpr int kHistSmem = 256 * kHistBinStride;             // 64 KB
 __device__ __forceinline__ void hist_count_word(uint8_t* bins, uint32_t w, uint32_t lane4)
@@ -92,8 +95,9 @@ hgi_hist_kernel(const uint8_t* __restrict__ data, uint32_t w, uint32_t h, uint32
         for (uint32_t y = y0; y < y1; ++y) hist_count_run(base + (size_t)y * pitch, w, bins, lane4, tid);
     }
     __syncthreads();
-    // warp k reduces bins [32k, 32k+32): lane-parallel reads of one bin row, shuffle tree
-    for (int bin = (tid >> 5) * 32; bin < (tid >> 5) * 32 + 32; ++bin) {
+    // warp k reduces its share of the bins: lane-parallel reads of one bin row, shuffle tree
+    constexpr int kBinsPerWarp = 256 / (HT / 32);
+    for (int bin = (tid >> 5) * kBinsPerWarp; bin < (tid >> 5) * kBinsPerWarp + kBinsPerWarp; ++bin) {
 #ifndef HGI_VAR_HIST_NOSWZ
         uint32_t v = *reinterpret_cast<const uint32_t*>(bins + (bin ^ (int)(2u * lane4)) * kHistBinStride + lane4);
 #else
@@ -278,8 +282,8 @@ cudaError_t launch_histogram(const uint8_t* data, uint32_t w, uint32_t h, uint32
     cudaError_t e = cudaMemsetAsync(hist_out, 0, (size_t)n_images * 256 * sizeof(uint32_t), stream);
     const uint64_t n_per_image = (uint64_t)w * h;
     if (e != cudaSuccess || n_per_image == 0) return e;
-    // Zeroing and reducing the 32 KB of counters costs a block about as much as counting 32 KB of data: give every
-    // block 256 KiB when the job is large, and not less than 32 KiB (a single small plane still spreads over the chip)
+    // Zeroing and reducing the 32 KB of counters costs a block about as much as counting 32 KB of data: a block gets
+    // 1 MiB when the job is large; smaller jobs are cut so that every SM still has blocks (not below 64 KiB)
     {   // function attributes are per device: opt in to 64 KB of dynamic shared memory once on each
         static bool done[64] = {};
         int dev = 0;
@@ -291,7 +295,9 @@ cudaError_t launch_histogram(const uint8_t* data, uint32_t w, uint32_t h, uint32
         }
     }
     const uint64_t total = n_per_image * n_images;
-    const uint64_t per_block = total >= (512ull << 20) ? (256u << 10) : (total >= (32ull << 20) ? (64u << 10) : (32u << 10));
+    uint64_t per_block = ((total / 592 + 16383) / 16384) * 16384;            // ~4 blocks per SM
+    if (per_block < (64u << 10)) per_block = 64u << 10;
+    if (per_block > ((uint64_t)HGI_HIST_BLOCK_KB << 10)) per_block = (uint64_t)HGI_HIST_BLOCK_KB << 10;
     uint64_t bpi = (n_per_image + per_block - 1) / per_block;
     if (bpi < 1) bpi = 1;
     if (pitch != w && bpi > h) bpi = h;
