@@ -66,13 +66,14 @@ namespace {
 // chunk are still inside the plane batch) / aligned middle words plus byte head and tail for stores; ragged chunks
 // at the right image edge use byte accesses.  Bytes beyond the image read as 0 and are never written.
 // Zero the bytes of an aligned chunk that lie in the row padding (nvalid..15).  Deliberately not inlined, see load_chunk.
-__device__ __noinline__ void mask_padding(uint4& a, int nvalid)
+__device__ __noinline__ uint4 mask_padding(uint4 a, int nvalid)   // by value: arguments and result travel in registers
 {
     const uint32_t nb = (uint32_t)min(nvalid, 16);
     a.x &= nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
     a.y &= nb >= 8 ? 0xFFFFFFFFu : (nb <= 4 ? 0u : ((1u << (8 * (nb - 4))) - 1u));
     a.z &= nb >= 12 ? 0xFFFFFFFFu : (nb <= 8 ? 0u : ((1u << (8 * (nb - 8))) - 1u));
     a.w &= nb >= 16 ? 0xFFFFFFFFu : (nb <= 12 ? 0u : ((1u << (8 * (nb - 12))) - 1u));
+    return a;
 }
 
 // `ragged` (CTA-uniform, from the launch arguments): rows are padded and the width is not a multiple of 16, so an
@@ -85,7 +86,7 @@ __device__ __forceinline__ uint4 load_chunk(const uint8_t* __restrict__ ptr, int
     if (ALIGNED) {
         // padded rows: the chunk is in memory as a whole, bytes beyond the image are the caller's padding -> read as 0
         uint4 a = __ldg(reinterpret_cast<const uint4*>(ptr));
-        if (ragged) mask_padding(a, nvalid);   // a call the compiler cannot predicate: whole-chunk planes skip it with one branch
+        if (ragged) a = mask_padding(a, nvalid);   // a call the compiler cannot predicate: whole-chunk planes skip it with one branch
         return a;
     }
     const uint32_t sh = (uint32_t)((uintptr_t)ptr & 3u);
