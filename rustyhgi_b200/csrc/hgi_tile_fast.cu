@@ -148,9 +148,12 @@ __device__ __forceinline__ FastSmem& opaque_smem(FastSmem& s)
 #endif
 }
 
-// EDGE = false: the tile and its whole halo lie inside the image, so every extent is a compile-time constant
+// EDGE = 0: the tile and its whole halo lie inside the image, so every extent is a compile-time constant
+// EDGE = 2: a tile of the right tile column of a plane whose width is a multiple of the tile width, in a tile row whose
+//           halo rows are inside the image: exactly TW columns (no right halo), all rows -- constants again
+// EDGE = 1: anything else
 // and all the in-image predicates (loads, stores, fringe cells, masks) fold away.
-template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED, bool EDGE>
+template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED, int EDGE>
 __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint32_t tx, uint32_t ty)
 {
     constexpr int F = 1 << NLEV;
@@ -160,14 +163,14 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
 #endif
     const uint32_t img = blockIdx.z;
     const uint32_t X0 = tx * TW, Y0 = ty * TH;
-    const int xin = EDGE ? (int)min((uint32_t)(TW + FMAX + 1), p.w - X0) : TW + FMAX + 1;   // in-image extent of tile + halo
-    const int yin = EDGE ? (int)min((uint32_t)(TH + FMAX + 1), p.h - Y0) : TH + FMAX + 1;
-    const bool edge = EDGE;
+    const int xin = EDGE == 1 ? (int)min((uint32_t)(TW + FMAX + 1), p.w - X0) : (EDGE == 2 ? TW : TW + FMAX + 1);   // in-image extent of tile + halo
+    const int yin = EDGE == 1 ? (int)min((uint32_t)(TH + FMAX + 1), p.h - Y0) : TH + FMAX + 1;
+    const bool edge = EDGE != 0;
     const size_t tile_off = ((size_t)img * p.h + Y0) * p.pitch + X0;   // CTA-uniform; the same in the source and output planes
     const size_t pitch = (size_t)p.pitch;
     const uint8_t* __restrict__ tile = p.src + tile_off;
     const bool top = (p.c_recon == nullptr);
-    const bool ragged = EDGE && ALIGNED && p.vec_ok == 2u;   // padded rows whose width is not a multiple of 16
+    const bool ragged = EDGE == 1 && ALIGNED && p.vec_ok == 2u;   // padded rows whose width is not a multiple of 16
     const QuantSwar qc = {p.q_one, p.q_mul, p.q_add, p.q_shift, p.q_scale, p.q_rmask, p.q_qmul, p.q_hK, p.q_hc1, p.q_hS, p.q_hc2};   // filled by the launcher
 
 #ifdef HGI_VAR_POISON_SMEM
@@ -191,8 +194,8 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     for (int u = 0; u < NU; ++u) {
         const int y = 2 * (NU * ry + u);
         // a complete chunk may be over-read by <= 3 bytes unless it ends the very last row of the batch
-        const bool last0 = EDGE && (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 1 >= p.h) && (X0 + 16u * sx + 16u >= p.pitch);
-        const bool last1 = EDGE && (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 2 >= p.h) && (X0 + 16u * sx + 16u >= p.pitch);
+        const bool last0 = EDGE != 0 && (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 1 >= p.h) && (X0 + 16u * sx + 16u >= p.pitch);
+        const bool last1 = EDGE != 0 && (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 2 >= p.h) && (X0 + 16u * sx + 16u >= p.pitch);
         ev[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * u) * p.pitch, y < yin ? nvalid : 0, !last0, ragged);
         od[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * u + 1) * p.pitch, y + 1 < yin ? nvalid : 0, !last1, ragged);
     }
@@ -384,36 +387,28 @@ hgi_tile_fast_kernel(const PassArgs p)
     if (kSplit) {
         const bool interior = (blockIdx.x + 1) * TW + FMAX + 1 <= p.w && (blockIdx.y + 1) * TH + FMAX + 1 <= p.h;
         if (interior) {
-            tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, false>(p, sm, blockIdx.x, blockIdx.y);
+            tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 0>(p, sm, blockIdx.x, blockIdx.y);
             return;
         }
     }
-    tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, true>(p, sm, blockIdx.x, blockIdx.y);
+    tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 1>(p, sm, blockIdx.x, blockIdx.y);
 }
 
-// The same pass as two launches: PART 1 = the interior tiles [0, fast_itx) x [0, fast_ity) with the predicate-free
-// body, PART 2 = the remaining bottom rows and right columns of tiles, enumerated along blockIdx.x.
+// The same pass as three launches with two-dimensional tile grids (no index arithmetic in the kernel):
+// PART 1 = the interior tiles [0, fast_itx) x [0, fast_ity) with the predicate-free body;
+// PART 2 = the right tile columns [fast_itx, tiles_x) of the interior tile rows, general edge body;
+// PART 4 = the same when there is ONE right column and it is exactly TW wide (width % TW == 0): constants again;
+// PART 3 = the bottom tile rows [fast_ity, tiles_y), all columns, general edge body.
 template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED, int PART>
 __global__ void __launch_bounds__(NT, (IDENTITY && !EXTRA && ALIGNED && NLEV == 4) ? HGI_FAST_MIN_BLOCKS_LIGHT : HGI_FAST_MIN_BLOCKS)
 hgi_tile_fast_part_kernel(const PassArgs p)
 {
     __shared__ FastSmem sm_static;
     FastSmem& sm = opaque_smem(sm_static);
-    if (PART == 1) {
-        tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, false>(p, sm, blockIdx.x, blockIdx.y);
-    } else {
-        const uint32_t idx = blockIdx.x, nright = (p.fast_tx - p.fast_itx) * p.fast_ity;
-        uint32_t tx, ty;
-        if (idx < nright) {                 // right columns of the interior rows
-            ty = idx / (p.fast_tx - p.fast_itx);
-            tx = p.fast_itx + (idx - ty * (p.fast_tx - p.fast_itx));
-        } else {                            // complete bottom rows
-            const uint32_t j = idx - nright;
-            ty = p.fast_ity + j / p.fast_tx;
-            tx = j - (j / p.fast_tx) * p.fast_tx;
-        }
-        tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, true>(p, sm, tx, ty);
-    }
+    if (PART == 1) tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 0>(p, sm, blockIdx.x, blockIdx.y);
+    else if (PART == 2) tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 1>(p, sm, p.fast_itx + blockIdx.x, blockIdx.y);
+    else if (PART == 4) tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 2>(p, sm, p.fast_itx + blockIdx.x, blockIdx.y);
+    else tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 1>(p, sm, blockIdx.x, p.fast_ity + blockIdx.y);
 }
 
 // below this many tiles (about four waves of 10 CTAs on 148 SMs) the second launch costs more than the edge predicates
@@ -430,10 +425,18 @@ cudaError_t launch_fast_split(PassArgs& a, uint32_t tiles_x, uint32_t tiles_y, c
         const dim3 nb(a.fast_itx, a.fast_ity, a.n_images);
         hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 1><<<nb, NT, 0, stream>>>(a); ++launch_count();
     }
-    const uint32_t nedge = tiles_x * tiles_y - a.fast_itx * a.fast_ity;
-    if (nedge) {
-        const dim3 nb(nedge, 1, a.n_images);
-        hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 2><<<nb, NT, 0, stream>>>(a); ++launch_count();
+    const uint32_t ncr = tiles_x - a.fast_itx, nbr = tiles_y - a.fast_ity;
+    if (ncr && a.fast_ity) {   // right tile columns of the interior tile rows
+        const dim3 nb(ncr, a.fast_ity, a.n_images);
+        if (ncr == 1 && a.w == tiles_x * (uint32_t)TW) {
+            hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 4><<<nb, NT, 0, stream>>>(a); ++launch_count();
+        } else {
+            hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 2><<<nb, NT, 0, stream>>>(a); ++launch_count();
+        }
+    }
+    if (nbr) {                 // bottom tile rows
+        const dim3 nb(tiles_x, nbr, a.n_images);
+        hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 3><<<nb, NT, 0, stream>>>(a); ++launch_count();
     }
     return cudaGetLastError();
 }

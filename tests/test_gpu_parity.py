@@ -118,7 +118,7 @@ def test_aligned_multi_tile_planes(ctxs, path):
 
 def test_interior_and_edge_tile_split(ctxs):
     """The SWAR kernel runs interior tiles (tile + 17-pixel halo inside the plane) through a predicate-free body --
-    a branch for the light kernels, a launch of its own for the quantizing encode once the job has >= 5920 tiles.
+    a branch for the light kernels, launches of their own (interior / right tile columns / bottom tile rows) for the quantizing encode once the job has >= 5920 tiles.
     Sizes on either side of every boundary: no interior tile, one, an interior column without an interior row."""
     ctx = ctxs["tile"]
     for w in (144, 160, 272, 288, 400):           # 128-wide tiles: interior columns = (w - 17) // 128
@@ -128,7 +128,7 @@ def test_interior_and_edge_tile_split(ctxs):
                 check_case(ctx, img, 4, q)
             check_case(ctx, img, 4, 1, interp=oc.INTERP_LEFTTOP)
     dec = hgi.Decoder(hgi.Crossed, ctx=ctx)
-    for (w, h) in [(144, 81), (160, 80), (160, 81), (272, 145), (288, 146), (416, 209)]:
+    for (w, h) in [(144, 81), (160, 80), (160, 81), (272, 145), (288, 146), (416, 209), (256, 145), (384, 146), (128, 200)]:
         tiles = -(-w // 128) * -(-h // 64)
         n = -(-5920 // tiles) + 3                  # enough tiles for the two-launch path
         base = np.stack([photo_like(w, h, seed=s + w) for s in range(6)] +
@@ -139,7 +139,9 @@ def test_interior_and_edge_tile_split(ctxs):
             launches0 = ctx.kernel_launches
             grids, hist = enc.encode_batch(imgs, want_hist=True)
             interior = ((w - 17) // 128) * ((h - 17) // 64) > 0
-            assert ctx.kernel_launches - launches0 == (3 if interior else 2), (w, h)   # [interior +] edge + histogram
+            # [interior + right tile columns +] bottom tile rows + histogram (a right column that is exactly one tile
+            # wide -- w % 128 == 0 -- runs the body specialised for it)
+            assert ctx.kernel_launches - launches0 == (4 if interior else 2), (w, h)
             want = oc.encode_batch(imgs[:len(base)], 4, qlevel=q)
             assert (grids == want[np.arange(n) % len(base)]).all(), (w, h, q)
             assert (hist[n - 1] == np.bincount(want[(n - 1) % len(base)].reshape(-1), minlength=256)).all()
