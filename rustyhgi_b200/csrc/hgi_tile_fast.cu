@@ -200,20 +200,48 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
         od[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * u + 1) * p.pitch, y + 1 < yin ? nvalid : 0, !last1, ragged);
     }
 
-    // halo chunks (right of / below the tile) feed only the coarse planes; the upper half of the CTA
-    // fetches them: TH/2 right-halo chunks (rows 0,2,..,TH-2; column TW) + rows TH, TH+4, TH+8 (chunks 0..8)
-    constexpr int NRIGHT = TH / 2, NHALO = NRIGHT + 27;
+    // halo chunks (right of / below the tile) feed only the coarse planes: TH/2 right-halo chunks (rows 0,2,..,TH-2;
+    // column TW) + rows TH, TH+4, TH+8 (chunks 0..8).  Two ways to fetch and stage them, chosen per kernel by A/B
+    // (2048 frames, same box): spread over the upper half of the CTA, one chunk per thread (decode 1.258 ms, encode
+    // Medium 1.681, encode Lossless 1.274), or all on the LAST WARP, NRIGHT/32 + 1 chunks per lane, so that the other
+    // warps skip the block with one uniform branch (1.266 / 1.722 / 1.242): the identity encode takes the second.
+    constexpr bool HALO_WARP = (MODE == kModeEncode) && IDENTITY;
+    constexpr int NRIGHT = TH / 2, NHALO = NRIGHT + 27, NRL = NRIGHT / 32;
+    // -- spread form
     const int hj = tid - (NT - (TH == 64 ? 64 : 128));
     int hy = 2 * hj, hc = 8;
-    if (hj >= NRIGHT) {
-        const int r = (hj - NRIGHT) / 9;
-        hc = (hj - NRIGHT) - 9 * r;
-        hy = TH + 4 * r;
-    }
-    const bool halo = NLEV > 1 && hj >= 0 && hj < NHALO;
+    bool halo = false;
     uint4 hv = make_uint4(0u, 0u, 0u, 0u);
-    if (halo && hy < yin) {
-        hv = load_chunk<ALIGNED>(tile + (uint32_t)hy * p.pitch + (uint32_t)(16 * hc), min(16, xin - 16 * hc), false, ragged);
+    // -- last-warp form
+    const bool halo_warp = HALO_WARP && NLEV > 1 && tid >= NT - 32;
+    const int hl = tid - (NT - 32);                     // lane of the halo warp
+    uint4 hvr[NRL], hvb = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int k = 0; k < NRL; ++k) hvr[k] = make_uint4(0u, 0u, 0u, 0u);
+    int hyb = TH, hcb = 0;
+    bool has_b = false;
+    if (!HALO_WARP) {
+        if (hj >= NRIGHT) {
+            const int r = (hj - NRIGHT) / 9;
+            hc = (hj - NRIGHT) - 9 * r;
+            hy = TH + 4 * r;
+        }
+        halo = NLEV > 1 && hj >= 0 && hj < NHALO;
+        if (halo && hy < yin)
+            hv = load_chunk<ALIGNED>(tile + (uint32_t)hy * p.pitch + (uint32_t)(16 * hc), min(16, xin - 16 * hc), false, ragged);
+    } else if (halo_warp) {
+#pragma unroll
+        for (int k = 0; k < NRL; ++k) {
+            const int y = 2 * (hl + 32 * k);
+            if (y < yin) hvr[k] = load_chunk<ALIGNED>(tile + (uint32_t)y * p.pitch + (uint32_t)TW, min(16, xin - TW), false, ragged);
+        }
+        if (hl < 27) {
+            const int r = (hl >= 9) + (hl >= 18);
+            has_b = true;
+            hcb = hl - 9 * r;
+            hyb = TH + 4 * r;
+            if (hyb < yin) hvb = load_chunk<ALIGNED>(tile + (uint32_t)hyb * p.pitch + (uint32_t)(16 * hcb), min(16, xin - 16 * hcb), false, ragged);
+        }
     }
 
     // ---- 2. stage the dense coarse planes + the coarse lattice of this pass ---------------------
@@ -225,6 +253,11 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
 #pragma unroll
     for (int u = 0; u < NU; ++u) stage_chunk<F, OWN2>(sm.P, ev[u], 2 * (NU * ry + u), sx);
     if (halo) stage_chunk<F>(sm.P, hv, hy, hc);
+    if (halo_warp) {
+#pragma unroll
+        for (int k = 0; k < NRL; ++k) stage_chunk<F>(sm.P, hvr[k], 2 * (hl + 32 * k), 8);
+        if (has_b) stage_chunk<F>(sm.P, hvb, hyb, hcb);
+    }
     if (NLEV == 4 && top) {
         // top pass with step-16 seeds (src/encoder.rs:26-37 / src/decoder.rs:22-28): the seed of lattice point
         // (16*ci, 16*cj) is byte 0 of a chunk some thread already holds; only x = TW+16 and y = TH+16 need a load
@@ -242,6 +275,20 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
         if (halo && (hy & 15) == 0 && hy <= TH) {
             Pf[(hy >> 4) * pf + hc] = (uint8_t)hv.x;
             if (MODE == kModeEncode) Qf[(hy >> 4) * pf + hc] = (uint8_t)hv.x;
+        }
+        if (halo_warp) {   // seeds at column TW (rows that are multiples of 16) and on row TH
+#pragma unroll
+            for (int k = 0; k < NRL; ++k) {
+                const int y = 2 * (hl + 32 * k);
+                if ((y & 15) == 0) {
+                    Pf[(y >> 4) * pf + 8] = (uint8_t)hvr[k].x;
+                    if (MODE == kModeEncode) Qf[(y >> 4) * pf + 8] = (uint8_t)hvr[k].x;
+                }
+            }
+            if (has_b && hyb == TH) {
+                Pf[(TH >> 4) * pf + hcb] = (uint8_t)hvb.x;
+                if (MODE == kModeEncode) Qf[(TH >> 4) * pf + hcb] = (uint8_t)hvb.x;
+            }
         }
         constexpr int last_ci = TW / 16 + 1, last_cj = TH / 16 + 1;
         if (tid < last_ci + last_cj + 1) {
