@@ -499,7 +499,12 @@ def run_ours(args, rank, world, local_rank):
     extra = None
     if not args.no_extra:
         encs[1].encode_device(frames, grids_out=grids)             # Medium grids for the histogram block
-        extra = extra_block(hgi, ctx, dev, rank, world, dist, measured_peak()[0], grids, barrier)
+        try:
+            extra = extra_block(hgi, ctx, dev, rank, world, dist, measured_peak()[0], grids, barrier)
+        except Exception as exc:                                   # the headline line must survive a failing side measurement
+            if world > 1:
+                raise                                              # ranks would lose step with each other: fail loudly instead
+            extra = {"error": f"{type(exc).__name__}: {exc}"}
         if strong:
             extra["strong_scaling"] = strong
 

@@ -112,6 +112,7 @@ extern "C" {
                                     params: *const hgi_params_t, grids_out: *mut u8, hist_out: *mut u32) -> c_int;
     pub fn hgi_pool_decode_batch_u8(pool: *mut hgi_pool_t, grids: *const u8, n_images: u32, width: u32, height: u32,
                                     params: *const hgi_params_t, images_out: *mut u8) -> c_int;
+    pub fn hgi_plan_bands(height: u32, levels: u32, n_bands: u32, bands_out: *mut hgi_band_t, n_bands_out: *mut c_int) -> c_int;
     pub fn hgi_pool_plan_bands(pool: *const hgi_pool_t, height: u32, levels: u32, bands_out: *mut hgi_band_t,
                                n_bands_out: *mut c_int) -> c_int;
     pub fn hgi_pool_encode_plane_u8(pool: *mut hgi_pool_t, image: *const u8, width: u32, height: u32,

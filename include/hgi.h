@@ -229,6 +229,10 @@ typedef struct {
 } hgi_band_t;
 int hgi_pool_plan_bands(const hgi_pool_t *pool, uint32_t height, uint32_t levels,
                         hgi_band_t *bands_out /* [hgi_pool_size()] */, int *n_bands_out);
+/* The same plan for any number of bands (pure host arithmetic, no device needed): what a caller that runs one
+   process per GPU uses to find the rows of its rank. */
+int hgi_plan_bands(uint32_t height, uint32_t levels, uint32_t n_bands, hgi_band_t *bands_out /* [n_bands] */,
+                   int *n_bands_out);
 int hgi_pool_encode_plane_u8(hgi_pool_t *pool, const uint8_t *image, uint32_t width, uint32_t height,
                              const hgi_params_t *params, uint8_t *grid_out);
 int hgi_pool_decode_plane_u8(hgi_pool_t *pool, const uint8_t *grid, uint32_t width, uint32_t height,

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "hgi_pool_synchronize": (_int, [_vp]),
     "hgi_pool_encode_batch_u8": (_int, [_vp, _vp, _u32, _u32, _u32, _pp, _vp, _vp]),
     "hgi_pool_decode_batch_u8": (_int, [_vp, _vp, _u32, _u32, _u32, _pp, _vp]),
+    "hgi_plan_bands": (_int, [_u32, _u32, _u32, _vp, ctypes.POINTER(_int)]),
     "hgi_pool_plan_bands": (_int, [_vp, _u32, _u32, _vp, ctypes.POINTER(_int)]),
     "hgi_pool_encode_plane_u8": (_int, [_vp, _vp, _u32, _u32, _pp, _vp]),
     "hgi_pool_decode_plane_u8": (_int, [_vp, _vp, _u32, _u32, _pp, _vp]),

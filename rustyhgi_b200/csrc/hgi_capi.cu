@@ -1251,6 +1251,13 @@ int hgi_pool_decode_batch_u8(hgi_pool_t* pool, const uint8_t* grids, uint32_t n_
     return pool_batch(pool, hgi::kModeDecode, grids, n_images, width, height, params, images_out, nullptr);
 }
 
+int hgi_plan_bands(uint32_t height, uint32_t levels, uint32_t n_bands, hgi_band_t* bands_out, int* n_bands_out)
+{
+    if (!bands_out || !n_bands_out || levels > HGI_MAX_LEVELS || n_bands == 0) return HGI_ERR_INVALID_ARG;
+    *n_bands_out = plan_bands(height, levels, n_bands, bands_out);
+    return HGI_OK;
+}
+
 int hgi_pool_plan_bands(const hgi_pool_t* pool, uint32_t height, uint32_t levels, hgi_band_t* bands_out, int* n_bands_out)
 {
     if (!pool || !bands_out || !n_bands_out || levels > HGI_MAX_LEVELS) return HGI_ERR_INVALID_ARG;

@@ -101,3 +101,21 @@ def test_world_size_2_gloo():
         p.join(60)
         assert p.exitcode == 0
     assert res == (True, True, 2.0)
+
+
+def test_c_abi_band_plan_equals_the_python_one():
+    """hgi_plan_bands (what hgi_pool_* uses; pure host arithmetic, callable without a GPU) == sharding.plan_bands."""
+    import ctypes
+    import rustyhgi_b200 as hgi
+    from rustyhgi_b200 import _lib
+    L = hgi.lib()
+    for height in (1, 255, 256, 257, 1000, 16384, 16385, 100000):
+        for levels in (0, 1, 4, 8, 12, 31):
+            for n in (1, 2, 3, 8, 17):
+                bands = (_lib.BandStruct * n)()
+                cnt = ctypes.c_int(-1)
+                assert L.hgi_plan_bands(height, levels, n, ctypes.cast(bands, ctypes.c_void_p), ctypes.byref(cnt)) == 0
+                want = hgi.sharding.plan_bands(height, levels, n)
+                got = [(bands[i].y0, bands[i].y1, bands[i].in_y1) for i in range(cnt.value)]
+                assert got == [(b.y0, b.y1, b.in_y1) for b in want], (height, levels, n)
+    assert L.hgi_plan_bands(100, 32, 2, ctypes.cast((_lib.BandStruct * 2)(), ctypes.c_void_p), ctypes.byref(ctypes.c_int())) == -1
