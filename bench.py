@@ -567,8 +567,8 @@ def run_ours(args, rank, world, local_rank):
         dom = "encode_medium"
         achieved = alg_bytes / (per[dom] * 1e-3) / 1e9
         traffic = profiled_traffic()
-        roofline = {"bound": "hbm", "kernel": "hgi_tile_fast_part_kernel<encode, Crossed, Linear> (Medium): interior-tile launch + edge-tile "
-                              "launch of one encode, timed together",
+        roofline = {"bound": "hbm", "kernel": "hgi_tile_fast_part_kernel<encode, Crossed, Linear> (Medium): interior-tile launch + right-tile-column "
+                              "launch + bottom-tile-row launch of one encode, timed together",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                     "algorithmic_bytes_per_launch": alg_bytes,

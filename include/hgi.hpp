@@ -235,6 +235,66 @@ private:
     std::shared_ptr<Context> ctx_;
 };
 
+// The GPUs of one box behind one handle (hgi_pool_t): by image for batches, by row band for one
+// huge plane.  Results are byte-identical to a single context.
+class Pool {
+public:
+    // devices: CUDA ordinals (a device may be listed more than once); empty = every sm_100 device of the box
+    explicit Pool(const std::vector<int>& devices = {})
+    {
+        check(hgi_pool_create(devices.empty() ? nullptr : devices.data(), (int)devices.size(), &pool_), "hgi_pool_create");
+    }
+    ~Pool() { hgi_pool_destroy(pool_); }
+    Pool(const Pool&) = delete;
+    Pool& operator=(const Pool&) = delete;
+    int size() const { return hgi_pool_size(pool_); }
+    hgi_pool_t* get() const { return pool_; }
+
+    // `n` planes of width x height back to back in `images`; member k takes the k-th contiguous share
+    template <class I, class Q>
+    Bytes encode_batch(I, const Q& quantizator, size_t scale_level, const Bytes& images, uint32_t n, uint32_t width, uint32_t height)
+    {
+        if (images.size() != (size_t)n * width * height) throw Error(HGI_ERR_INVALID_ARG, "Pool::encode_batch");
+        Bytes grids(images.size());
+        const hgi_params_t p{(uint32_t)scale_level, I::id, Q::kind, (int32_t)quantizator.level()};
+        check(hgi_pool_encode_batch_u8(pool_, images.data(), n, width, height, &p, grids.data(), nullptr), "hgi_pool_encode_batch_u8");
+        return grids;
+    }
+    template <class I>
+    Bytes decode_batch(I, size_t levels, const Bytes& grids, uint32_t n, uint32_t width, uint32_t height)
+    {
+        if (grids.size() != (size_t)n * width * height) throw Error(HGI_ERR_INVALID_ARG, "Pool::decode_batch");
+        Bytes images(grids.size());
+        const hgi_params_t p{(uint32_t)levels, I::id, HGI_QUANT_NOOP, 0};
+        check(hgi_pool_decode_batch_u8(pool_, grids.data(), n, width, height, &p, images.data()), "hgi_pool_decode_batch_u8");
+        return images;
+    }
+    // ONE plane cut into row bands (multiples of 2^scale_level rows + 2^scale_level + 1 overlap rows, no exchange)
+    template <class I, class Q>
+    Grid encode_plane(I, const Q& quantizator, size_t scale_level, const GrayImage& input)
+    {
+        Grid grid;
+        grid.width = input.width;
+        grid.buffer.resize(input.data.size());
+        const hgi_params_t p{(uint32_t)scale_level, I::id, Q::kind, (int32_t)quantizator.level()};
+        check(hgi_pool_encode_plane_u8(pool_, input.data.data(), input.width, input.height, &p, grid.buffer.data()),
+              "hgi_pool_encode_plane_u8");
+        return grid;
+    }
+    template <class I>
+    GrayImage decode_plane(I, std::pair<uint32_t, uint32_t> dimensions, size_t levels, const Grid& grid)
+    {
+        GrayImage image(dimensions.first, dimensions.second, GrayImage::Uninitialized{});
+        if (grid.buffer.size() != image.data.size()) throw Error(HGI_ERR_INVALID_ARG, "Pool::decode_plane");
+        const hgi_params_t p{(uint32_t)levels, I::id, HGI_QUANT_NOOP, 0};
+        check(hgi_pool_decode_plane_u8(pool_, grid.buffer.data(), image.width, image.height, &p, image.data.data()),
+              "hgi_pool_decode_plane_u8");
+        return image;
+    }
+private:
+    hgi_pool_t* pool_ = nullptr;
+};
+
 // src/archive.rs:15-22
 struct Metadata {
     QuantizationLevel quantization_level = QuantizationLevel::Lossless;

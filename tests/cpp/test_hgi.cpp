@@ -75,6 +75,33 @@ static void bench_variants()   // the four encoder instantiations of benches/ben
     ASSERT(Decoder<LeftTop>(LeftTop{}).decode({192, 108}, 4, a).data == image.data);
 }
 
+static void pool_equals_single_context()   // by image and by row band, byte-identical to one context
+{
+    Pool pool({0, 0});                      // two contexts on device 0 (a box with several GPUs would list them)
+    ASSERT(pool.size() == 2);
+    const uint32_t w = 640, h = 700;
+    const GrayImage image = get_test_image(w, h);
+    const Linear q = Linear::from(QuantizationLevel::Medium);
+    const Grid one = Encoder<Crossed, Linear>(Crossed{}, q, 6).encode(image);
+    const Grid banded = pool.encode_plane(Crossed{}, q, 6, image);
+    ASSERT(banded == one);
+    ASSERT(pool.decode_plane(Crossed{}, {w, h}, 6, banded).data == Decoder<Crossed>(Crossed{}).decode({w, h}, 6, one).data);
+    Bytes batch((size_t)5 * w * h);
+    for (int k = 0; k < 5; ++k)
+        for (size_t i = 0; i < (size_t)w * h; ++i) batch[(size_t)k * w * h + i] = (uint8_t)(image.data[i] + 31 * k);
+    const Bytes grids = pool.encode_batch(Crossed{}, q, 4, batch, 5, w, h);
+    for (int k = 0; k < 5; ++k) {
+        GrayImage f(w, h);
+        std::memcpy(f.data.data(), batch.data() + (size_t)k * w * h, (size_t)w * h);
+        const Grid g = Encoder<Crossed, Linear>(Crossed{}, q, 4).encode(f);
+        ASSERT(std::memcmp(g.buffer.data(), grids.data() + (size_t)k * w * h, (size_t)w * h) == 0);
+    }
+    const Bytes back = pool.decode_batch(Crossed{}, 4, grids, 5, w, h);
+    int worst = 0;
+    for (size_t i = 0; i < back.size(); ++i) { const int d = (int)back[i] - (int)batch[i]; worst = std::max(worst, d < 0 ? -d : d); }
+    ASSERT(worst <= q.error());
+}
+
 int main()
 {
     test_error(QuantizationLevel::Lossless);   // lossless_compression  src/lib.rs:79-82
@@ -83,6 +110,7 @@ int main()
     test_error(QuantizationLevel::High);       // high_compression      :94-97
     serde();
     bench_variants();
+    pool_equals_single_context();
     std::printf("test_hgi: all reference unit tests passed on the GPU path (%llu kernel launches)\n",
                 (unsigned long long)Context::shared()->kernel_launches());
     return 0;
