@@ -144,8 +144,17 @@ __device__ __forceinline__ uint32_t pred_pk2(uint32_t A, uint32_t B, uint32_t C,
     const uint32_t x1 = (A ^ B) & 0x00010001u;
     const uint32_t w = x1 & (C ^ D) & (A ^ C);
     uint32_t t2, yb;
-    const uint32_t t3 = A + B + C;                                             // one IADD3 (the FMA pipe carries more of this path than the ALU pipe)
+#ifdef HGI_VAR_PRED_IADD3
+    const uint32_t t3 = A + B + C;                                             // one IADD3 (ALU pipe)
+#else
+    const uint32_t t3 = fadd(fadd(A, B, one), C, one);                         // two IMADs: one instruction more, but off the ALU pipe (-0.7 %, A/B)
+#endif
+#ifdef HGI_VAR_PRED_IADD7
+    t2 = D + D + 0x00070007u;   // one IADD3 with an immediate instead of IMAD + the move of the 2 into a register: fewer
+                                // instructions, but on the ALU pipe -- 1.5 % slower (A/B), the ALU pipe is the tighter one
+#else
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t2) : "r"(D), "r"(one + one), "r"(0x00070007u));
+#endif
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t2) : "r"(t3), "r"(one + one), "r"(t2));
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(yb) : "r"(w), "r"(4u * one), "r"(t2));
     if (WANT_P) p = hfma2(yb, kH_eighth, kH_511ulp);
