@@ -58,6 +58,9 @@ struct Scratch {
     DevBuf compact[4];   // ping-pong {recon, q} compact planes of the coarse passes
     DevBuf dec_in;       // decimated source of a coarse pass
     DevBuf level_recon;  // per-level path: reconstruction planes when the caller gives none
+    // fork/join of the independent split launches of the quantizing encode (hgi_kernels.h PassArgs::side_stream)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 struct Slot {
@@ -188,6 +191,9 @@ void free_scratch(Scratch& sc)
     for (auto& b : sc.compact) if (b.p) { cudaFree(b.p); b = DevBuf{}; }
     if (sc.dec_in.p) { cudaFree(sc.dec_in.p); sc.dec_in = DevBuf{}; }
     if (sc.level_recon.p) { cudaFree(sc.level_recon.p); sc.level_recon = DevBuf{}; }
+    if (sc.side) { cudaStreamDestroy(sc.side); sc.side = nullptr; }
+    if (sc.ev_fork) { cudaEventDestroy(sc.ev_fork); sc.ev_fork = nullptr; }
+    if (sc.ev_join) { cudaEventDestroy(sc.ev_join); sc.ev_join = nullptr; }
 }
 
 // Scratch set of a device-API caller stream (created on first use).
@@ -302,6 +308,21 @@ int run_tile_path(hgi_ctx* ctx, Scratch& sc, int mode, const uint8_t* src, uint3
         int rc = reserve(ctx, sc, sc.dec_in, max_compact);
         if (rc) return rc;
     }
+    // side stream + events for the split launches of the quantizing encode; created outside any capture (the first
+    // sighting of a chain runs uncaptured), a single-image job gains most (the edge launches are one wave each)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (mode == hgi::kModeEncode && qerr != 0 && !sc.side && st != cudaStreamLegacy &&
+        cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+        if (cudaStreamCreateWithFlags(&sc.side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&sc.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&sc.ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            (void)cudaGetLastError();
+            if (sc.side) { cudaStreamDestroy(sc.side); sc.side = nullptr; }
+            if (sc.ev_fork) { cudaEventDestroy(sc.ev_fork); sc.ev_fork = nullptr; }
+            if (sc.ev_join) { cudaEventDestroy(sc.ev_join); sc.ev_join = nullptr; }
+        }
+    }
+    (void)cudaGetLastError();
     if (max_compact && poison_scratch() >= 0) {
         // debug hook (HGI_B200_POISON_SCRATCH=<byte>): the scratch planes start as a known pattern; results must not change
         for (auto& b : sc.compact)
@@ -335,6 +356,11 @@ int run_tile_path(hgi_ctx* ctx, Scratch& sc, int mode, const uint8_t* src, uint3
         if (ps.d_log2 == 0) {
             a.grid_out = grid_out;
             a.recon_out = recon_out;
+            if (st != cudaStreamLegacy && sc.side && sc.ev_fork && sc.ev_join) {
+                a.side_stream = sc.side;
+                a.ev_fork = sc.ev_fork;
+                a.ev_join = sc.ev_join;
+            }
             a.vec_ok = (pitch % 16 == 0) && aligned16(src) && (grid_out == nullptr || aligned16(grid_out)) &&
                        (recon_out == nullptr || aligned16(recon_out));
             if (a.vec_ok && (w % 16 != 0)) a.vec_ok = 2;   // padded rows: the last chunk of a row holds padding

@@ -39,6 +39,11 @@ struct PassArgs {
     // SWAR quantizer constants (quant_swar() of hgi_tile_swar.cuh, evaluated on the host per launch)
     uint32_t q_one, q_mul, q_add, q_shift, q_scale, q_rmask, q_qmul;
     uint32_t q_hK, q_hc1, q_hS, q_hc2;   // fp16x2 form
+    // Split launches of the quantizing encode (interior / right tile columns / bottom tile rows) are independent of each
+    // other: with a side stream and two events (owned by the caller's scratch set; all null = run them in sequence) the
+    // two small edge launches run next to the interior launch instead of after it.
+    cudaStream_t side_stream;
+    cudaEvent_t ev_fork, ev_join;
 };
 
 // Dispatch of one pass.  kTileAuto: D == 1 passes on 16-byte-aligned planes go to the register-prefetch SWAR

@@ -468,6 +468,14 @@ cudaError_t launch_fast_split(PassArgs& a, uint32_t tiles_x, uint32_t tiles_y, c
     a.fast_itx = a.w >= (uint32_t)(FMAX + 1) ? min(tiles_x, (a.w - (FMAX + 1)) / TW) : 0u;
     a.fast_ity = a.h >= (uint32_t)(FMAX + 1) ? min(tiles_y, (a.h - (FMAX + 1)) / TH) : 0u;
     if (a.fast_itx == 0 || a.fast_ity == 0) a.fast_itx = a.fast_ity = 0;
+    // the edge launches depend on nothing the interior launch writes: fork them onto the side stream when there is one
+    const bool fork = a.fast_itx && a.side_stream && a.ev_fork && a.ev_join;
+    cudaStream_t es = fork ? a.side_stream : stream;
+    if (fork) {
+        cudaError_t e = cudaEventRecord(a.ev_fork, stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(a.side_stream, a.ev_fork, 0);
+        if (e != cudaSuccess) return e;
+    }
     if (a.fast_itx) {
         const dim3 nb(a.fast_itx, a.fast_ity, a.n_images);
         hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 1><<<nb, NT, 0, stream>>>(a); ++launch_count();
@@ -476,14 +484,19 @@ cudaError_t launch_fast_split(PassArgs& a, uint32_t tiles_x, uint32_t tiles_y, c
     if (ncr && a.fast_ity) {   // right tile columns of the interior tile rows
         const dim3 nb(ncr, a.fast_ity, a.n_images);
         if (ncr == 1 && a.w == tiles_x * (uint32_t)TW) {
-            hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 4><<<nb, NT, 0, stream>>>(a); ++launch_count();
+            hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 4><<<nb, NT, 0, es>>>(a); ++launch_count();
         } else {
-            hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 2><<<nb, NT, 0, stream>>>(a); ++launch_count();
+            hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 2><<<nb, NT, 0, es>>>(a); ++launch_count();
         }
     }
     if (nbr) {                 // bottom tile rows
         const dim3 nb(tiles_x, nbr, a.n_images);
-        hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 3><<<nb, NT, 0, stream>>>(a); ++launch_count();
+        hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 3><<<nb, NT, 0, es>>>(a); ++launch_count();
+    }
+    if (fork) {
+        cudaError_t e = cudaEventRecord(a.ev_join, a.side_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, a.ev_join, 0);
+        if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }
