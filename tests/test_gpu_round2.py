@@ -27,13 +27,14 @@ def ctx():
 
 @pytest.mark.parametrize("path", [hgi.PATH_TILE, hgi.PATH_TILE_GENERIC])
 def test_pitched_planes_any_width(path):
-    """Rows padded to a 16-byte multiple (and further): the padding bytes of the input are garbage and must not
-    influence anything; grid, reconstruction, decoded image and histogram equal the oracle on the packed plane."""
+    """Rows padded to a 16-byte multiple (and further, and to odd pitches that take the unaligned instantiation): the
+    padding bytes of the input are garbage and must not influence anything; grid, reconstruction, decoded image and histogram equal the oracle on the packed plane."""
     import torch
     c = hgi.Context(0, path)
     rng = np.random.default_rng(5)
     cases = [(2, 70, 1919, 4, 2, 0), (1, 65, 131, 3, 1, 16), (2, 129, 255, 5, 3, 0), (1, 33, 37, 6, 2, 32),
-             (1, 300, 1000, 9, 2, 0), (3, 64, 128, 4, 0, 48), (1, 17, 1, 2, 1, 0), (1, 200, 145, 4, 2, 0)]
+             (1, 300, 1000, 9, 2, 0), (3, 64, 128, 4, 0, 48), (1, 17, 1, 2, 1, 0), (1, 200, 145, 4, 2, 0),
+             (2, 70, 131, 4, 2, 5), (1, 90, 256, 5, 3, 3), (2, 40, 64, 3, 1, 1)]      # pitches that are not multiples of 16 (or 4)
     for (n, h, w, levels, q, extra) in cases:
         pitch = (w + 15) // 16 * 16 + extra
         imgs = np.stack([photo_like(w, h, 3 * k + w) for k in range(n)])
