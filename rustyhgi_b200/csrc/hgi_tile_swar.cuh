@@ -129,9 +129,17 @@ constexpr uint32_t kH_255_256 = 0x3BF83BF8u;      // 255/256: 0x0100 -> 0x00FF p
 
 // Crossed predictor for the quantizing encode: returns pk = 256 - pred per lane and, if WANT_P, p = pred + 512 (the
 // only consumer is bit 8 of q + p; the bias keeps the lane away from -0 when pred == 0); both clean.
-// pred = (T + 1 + 2w) >> 2 (see pred2 below) = RN((2T + 4w - 1) / 8): the argument is an odd multiple of 1/8,
-// so round-to-nearest never sees a tie and equals the floor.  The lanes carry yb = 2T + 4w + 7 (<= 2047 because
-// w = 1 needs mixed parities, i.e. T <= 1018), pred + 512 = RN(yb/8 + 511) and 256 - pred = RN(257 - yb/8).
+// pred = (T + 1 + 2w) >> 2 (see pred2 below) = floor((m + 1) / 4) with m = T + 2w <= 1022 (w = 1 needs mixed
+// parities, i.e. T <= 1018).  One HFMA2 divides and floors: with b = 1/4 - 2^-13 (fp16 0x33FF) the exact product is
+// m/4 - m/8192 = k + {-1/4, 0, 1/4, 1/2} - eps for m = 4k + {-1, 0, 1, 2}, 0 <= eps < 1/8 (eps > 0 whenever m > 0), so it
+// lies strictly inside (k - 3/8, k + 1/2): round-to-nearest gives k and never sees a tie.  pred + 512 = RN(m b + 512),
+// 256 - pred = RN(256 - m b).  The parity term needs only two LOP3: the parities of A^B and C^D are those of the
+// column sums A + B and C + D, which the sum needs anyway: w = ((A ^ C) & 1) & (A + B) & (C + D).
+// (Round 2, first form: lanes 2T + 4w + 7 times 1/8 -- one multiply-add, one constant move and one LOP3 more.)
+constexpr uint32_t kH_quarter_lo = 0x33FF33FFu;   // 1/4 - 2^-13
+constexpr uint32_t kH_neg_quarter_lo = 0xB3FFB3FFu;
+constexpr uint32_t kH_512ulp = 0x02000200u;
+constexpr uint32_t kH_256ulp = 0x01000100u;
 template <int INTERP, bool WANT_P>
 __device__ __forceinline__ uint32_t pred_pk2(uint32_t A, uint32_t B, uint32_t C, uint32_t D, uint32_t one, uint32_t& p)
 {
@@ -141,24 +149,24 @@ __device__ __forceinline__ uint32_t pred_pk2(uint32_t A, uint32_t B, uint32_t C,
         asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(pk) : "r"(A), "r"(0u - one), "r"(0x01000100u));
         return pk;
     }
+#ifdef HGI_VAR_PRED_YB
     const uint32_t x1 = (A ^ B) & 0x00010001u;
     const uint32_t w = x1 & (C ^ D) & (A ^ C);
     uint32_t t2, yb;
-#ifdef HGI_VAR_PRED_IADD3
-    const uint32_t t3 = A + B + C;                                             // one IADD3 (ALU pipe)
-#else
     const uint32_t t3 = fadd(fadd(A, B, one), C, one);                         // two IMADs: one instruction more, but off the ALU pipe (-0.7 %, A/B)
-#endif
-#ifdef HGI_VAR_PRED_IADD7
-    t2 = D + D + 0x00070007u;   // one IADD3 with an immediate instead of IMAD + the move of the 2 into a register: fewer
-                                // instructions, but on the ALU pipe -- 1.5 % slower (A/B), the ALU pipe is the tighter one
-#else
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t2) : "r"(D), "r"(one + one), "r"(0x00070007u));
-#endif
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t2) : "r"(t3), "r"(one + one), "r"(t2));
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(yb) : "r"(w), "r"(4u * one), "r"(t2));
     if (WANT_P) p = hfma2(yb, kH_eighth, kH_511ulp);
     return hfma2(yb, kH_neg_eighth, kH_257ulp);
+#else
+    const uint32_t va = fadd(A, B, one), vc = fadd(C, D, one);                 // column sums, lanes <= 510
+    const uint32_t w = ((A ^ C) & 0x00010001u) & va & vc;                      // two LOP3
+    uint32_t m = fadd(va, vc, one);                                            // T
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(m) : "r"(w), "r"(one + one), "r"(m));   // T + 2w <= 1022
+    if (WANT_P) p = hfma2(m, kH_quarter_lo, kH_512ulp);
+    return hfma2(m, kH_neg_quarter_lo, kH_256ulp);
+#endif
 }
 
 // src/interpolator.rs:43-54 per lane.  With avg(x,y) = (x+y+1)>>1 = (x + y + ((x^y)&1)) / 2, the sum of the

@@ -189,10 +189,11 @@ def f16_quant_constants(error):
 
 
 H_EIGHTH, H_NEG_EIGHTH, H_511ULP, H_257ULP, H_255_256 = 0x3000, 0xB000, 0x01FF, 0x0101, 0x3BF8
+H_QUARTER_LO, H_NEG_QUARTER_LO, H_512ULP, H_256ULP = 0x33FF, 0xB3FF, 0x0200, 0x0100
 
 
-def fp16_pred_pk(A, B, C, D):
-    """pred_pk2<Crossed>: (p + 512 lanes, pk lanes) from clean corner lanes."""
+def fp16_pred_pk_yb(A, B, C, D):
+    """pred_pk2<Crossed>, -DHGI_VAR_PRED_YB (the first fp16 form): lanes 2T + 4w + 7, times 1/8."""
     x1 = (A ^ B) & 0x00010001
     w = x1 & (C ^ D) & (A ^ C)
     yb = (2 * (A + B + C) + 2 * D + 0x00070007 + 4 * w) & U32
@@ -201,20 +202,44 @@ def fp16_pred_pk(A, B, C, D):
     return hfma2(yb, rep(H_EIGHTH), rep(H_511ULP)), hfma2(yb, rep(H_NEG_EIGHTH), rep(H_257ULP))
 
 
+def fp16_pred_pk(A, B, C, D):
+    """pred_pk2<Crossed>: (p + 512 lanes, pk lanes) from clean corner lanes: m = T + 2w, one HFMA2 by 1/4 - 2^-13."""
+    va, vc = (A + B) & U32, (C + D) & U32
+    w = ((A ^ C) & 0x00010001) & va & vc
+    m = (va + vc + 2 * w) & U32
+    assert (m & 0xFFFF) <= 1022 and (m >> 16) <= 1022
+    rep = lambda h: h | (h << 16)
+    return hfma2(m, rep(H_QUARTER_LO), rep(H_512ULP)), hfma2(m, rep(H_NEG_QUARTER_LO), rep(H_256ULP))
+
+
 def test_fp16_constants_are_what_the_header_says():
     assert _h2f(H_EIGHTH) == 0.125 and _h2f(H_NEG_EIGHTH) == -0.125 and _h2f(H_511ULP) == 511 * 2.0 ** -24
     assert _h2f(H_257ULP) == 257 * 2.0 ** -24 and _h2f(H_255_256) == 255 / 256
+    assert _h2f(H_QUARTER_LO) == 0.25 - 2.0 ** -13 and _h2f(H_NEG_QUARTER_LO) == -(0.25 - 2.0 ** -13)
+    assert _h2f(H_512ULP) == 512 * 2.0 ** -24 and _h2f(H_256ULP) == 256 * 2.0 ** -24
     for n in list(range(0, 2048, 7)) + [1023, 1024, 1025, 2047]:
         assert _h2f(n) == n * 2.0 ** -24                        # subnormals and the first normal binade share the ulp
+
+
+def test_fp16_divide_by_four_is_a_floor_for_every_sum():
+    """RN(m * (1/4 - 2^-13) + 512) == 512 + (m + 1) // 4 and RN(256 - m * (1/4 - 2^-13)) == 256 - (m + 1) // 4 for
+    every m = T + 2w the predictor can form (0..1022), and the parity term from the column sums equals the three-XOR
+    form for all 16 parity patterns."""
+    for m in range(0, 1023):
+        assert hfma_lane(m, H_QUARTER_LO, H_512ULP) == 512 + (m + 1) // 4, m
+        assert hfma_lane(m, H_NEG_QUARTER_LO, H_256ULP) == 256 - (m + 1) // 4, m
+    for A, B, C, D in itertools.product((0, 1, 2, 3, 254, 255), repeat=4):
+        assert (((A ^ C) & 1) & (A + B) & (C + D)) == ((A ^ B) & (C ^ D) & (A ^ C) & 1)
 
 
 def test_fp16_predictor_matches_reference():
     vals = [0, 1, 2, 3, 4, 5, 126, 127, 128, 129, 252, 253, 254, 255]
     for A, B, C, D in itertools.product(vals, repeat=4):
         A2, B2, C2, D2 = 255 - A, B ^ 1, (C + 77) & 255, D       # a different cell in the other lane
-        p, pk = fp16_pred_pk(A | (A2 << 16), B | (B2 << 16), C | (C2 << 16), D | (D2 << 16))
         r0, r1 = ref_pred(A, B, C, D), ref_pred(A2, B2, C2, D2)
-        assert (p & 0xFFFF, p >> 16) == (r0 + 512, r1 + 512) and (pk & 0xFFFF, pk >> 16) == (256 - r0, 256 - r1)
+        for form in (fp16_pred_pk, fp16_pred_pk_yb):
+            p, pk = form(A | (A2 << 16), B | (B2 << 16), C | (C2 << 16), D | (D2 << 16))
+            assert (p & 0xFFFF, p >> 16) == (r0 + 512, r1 + 512) and (pk & 0xFFFF, pk >> 16) == (256 - r0, 256 - r1)
     rng = np.random.default_rng(11)
     for v in rng.integers(0, 256, (20000, 8)):
         A, B, C, D, A2, B2, C2, D2 = (int(x) for x in v)
