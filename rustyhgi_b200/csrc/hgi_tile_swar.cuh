@@ -182,6 +182,15 @@ template <int INTERP, bool DIRTY = false>
 __device__ __forceinline__ uint32_t pred2(uint32_t A, uint32_t B, uint32_t C, uint32_t D, uint32_t one)
 {
     if (INTERP == kInterpLeftTop) return A;                                    // src/interpolator.rs:26
+#ifndef HGI_VAR_PRED2_SHIFT
+    {   // the same division as pred_pk2: RN(m (1/4 - 2^-13)) = (m + 1) >> 2, clean lanes; 2 ALU + 5 FMA instead of 5 + 4
+        const uint32_t va = fadd(A, B, one), vc = fadd(C, D, one);
+        const uint32_t w = ((A ^ C) & 0x00010001u) & va & vc;
+        uint32_t m = fadd(va, vc, one);
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(m) : "r"(w), "r"(one + one), "r"(m));
+        return hfma2(m, kH_quarter_lo, 0u);
+    }
+#endif
     const uint32_t x1 = (A ^ B) & 0x00010001u;
     const uint32_t w = x1 & (C ^ D) & (A ^ C);
     // (((T + 1) >> 1) + w) >> 1 == (T + 1 + 2 w) >> 2: the doubling rides on the multiply-add, one shift instead of two
@@ -476,6 +485,50 @@ __device__ __forceinline__ void level2_owner(FastSmem& sm, const uint4& r0, cons
     *reinterpret_cast<uint2*>(row + ps) = make_uint2(p2o[0], p2o[1]);
 }
 
+// One fringe word of the s = 2 level, reduced to the ONE point per cell the finest level reads (see fringe_cell): the
+// words of the fringe row (it < wpr: cell row TH/4) need their (x0+1, y0) points -- plane row TH/2, all of which the
+// last row of finest cells reads as its lower corners -- and the words of the fringe column (cell column TW/4) the
+// (x0, y0+1) point of their first cell -- plane column TW/2, the right corners of the last finest cell column.  One
+// code path for both (the 32 words share a warp): the point pair comes from the even-row word (bytes 1, 3) or from the
+// odd-row word (bytes 0, 2) by address and PRMT selector, one encode2 / decode2 instead of three, no symbols (the
+// symbols of fringe points are never output).  The even-row word is rebuilt as [A r A r]; in a column word the r
+// bytes land on plane columns TW/2 + 1, + 3 and the odd-row word carries r in its lanes (byte 0 = the point, bytes
+// 1..3 = lane padding / the second cell): nobody reads those.
+template <int MODE, int INTERP, bool IDENTITY>
+__device__ __forceinline__ void fringe2_word(FastSmem& sm, int it, const QuantSwar& qc, bool edge, int xin_s, int yin_s)
+{
+    constexpr int ps = plane_pitch(2), pc = plane_pitch(4), wpr = TW / 8, ncy = TH / 4;
+    const bool is_row = it < wpr;
+    const int g = is_row ? it : wpr, cy = is_row ? ncy : it - wpr;
+    const uint8_t* ct = sm.P + plane_off(4) + cy * pc + 2 * g;
+    const uint32_t cwt = (uint32_t)*reinterpret_cast<const uint16_t*>(ct) | ((uint32_t)ct[2] << 16);
+    const uint32_t cwb = (uint32_t)*reinterpret_cast<const uint16_t*>(ct + pc) | ((uint32_t)ct[pc + 2] << 16);
+    const uint32_t A = lanes01(cwt), C = lanes12(cwt), B = lanes01(cwb), D = lanes12(cwb);
+    uint8_t* ev = sm.P + plane_off(2) + (2 * cy) * ps + 4 * g;
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(is_row ? ev : ev + ps);
+    const uint32_t a = prmt(w, 0u, is_row ? 0x4341u : 0x4240u);
+    uint32_t r, wev;
+    if (MODE == kModeEncode) {
+        uint32_t p = 0u;
+        const uint32_t pk = pred_pk2<INTERP, !IDENTITY>(A, B, C, D, qc.one, p);
+#ifndef HGI_VAR_INTQ
+        (void)encode2<IDENTITY, false>(a, p, pk, qc, r);
+#else
+        (void)encode2<IDENTITY>(a, p, pk, qc, r);
+#endif
+        wev = interleave(A, r);
+    } else {
+        r = decode2(a, pred2<INTERP, true>(A, B, C, D, qc.one), qc.one);
+        wev = pack_lo(A, r);
+    }
+    if (edge) {   // out-of-image reconstruction must read as 0 (src/interpolator.rs:75-82)
+        wev &= valid_mask(4 * g, 2 * cy, xin_s, yin_s);
+        r &= valid_mask(4 * g, 2 * cy + 1, xin_s, yin_s);
+    }
+    *reinterpret_cast<uint32_t*>(ev) = wev;
+    if (!is_row) *reinterpret_cast<uint32_t*>(ev + ps) = r;
+}
+
 // One fringe cell (extra cell column / row right of and below the tile) of a coarse level, scalar.
 template <int MODE, int INTERP, bool IDENTITY, int S>
 __device__ __forceinline__ void fringe_cell(FastSmem& sm, int cx, int cy, const QuantSwar& qc, int xin_s, int yin_s)
@@ -571,8 +624,14 @@ __device__ __forceinline__ void coarse_level(FastSmem& sm, int tid, const QuantS
         // (32 words = one warp at S = 2); of the corner cell only the lattice point itself is read by anyone: a copy of
         // the coarser plane's byte (0 when out of the image)
         constexpr int nfw = wpr + ncy;
-        for (int it = GS - 1 - tid; it < nfw; it += GS)
+        for (int it = GS - 1 - tid; it < nfw; it += GS) {
+#ifdef HGI_VAR_FULL_FRINGE2
             level_word<MODE, INTERP, IDENTITY, S>(sm, it < wpr ? it : wpr, it < wpr ? ncy : it - wpr, qc, edge, xin_s, yin_s);
+#else
+            if (S == 2) fringe2_word<MODE, INTERP, IDENTITY>(sm, it, qc, edge, xin_s, yin_s);
+            else level_word<MODE, INTERP, IDENTITY, S>(sm, it < wpr ? it : wpr, it < wpr ? ncy : it - wpr, qc, edge, xin_s, yin_s);
+#endif
+        }
         if (tid == GS - 1)
             (sm.P + plane_off(S))[(2 * ncy) * plane_pitch(S) + 4 * wpr] = (sm.P + plane_off(2 * S))[ncy * plane_pitch(2 * S) + 2 * wpr];
     }

@@ -16,7 +16,7 @@ def ref_pred(A, B, C, D):
     return (avg(A, B) + avg(D, C) + avg(C, A) + avg(D, B)) >> 2
 
 
-def swar_pred(A, B, C, D):                                    # pred2<Crossed>
+def swar_pred(A, B, C, D):                                    # pred2<Crossed>, -DHGI_VAR_PRED2_SHIFT (integer shift form)
     x1 = (A ^ B) & 0x00010001
     w = x1 & (C ^ D) & (A ^ C)
     t1 = (A + B + C) + (D + 0x00010001)                       # T + 1 per lane
@@ -230,6 +230,25 @@ def test_fp16_divide_by_four_is_a_floor_for_every_sum():
         assert hfma_lane(m, H_NEG_QUARTER_LO, H_256ULP) == 256 - (m + 1) // 4, m
     for A, B, C, D in itertools.product((0, 1, 2, 3, 254, 255), repeat=4):
         assert (((A ^ C) & 1) & (A + B) & (C + D)) == ((A ^ B) & (C ^ D) & (A ^ C) & 1)
+
+
+def fp16_pred(A, B, C, D):
+    """pred2<Crossed> (decode): the same sum, RN(m * (1/4 - 2^-13)) with a zero addend -> clean lanes."""
+    va, vc = (A + B) & U32, (C + D) & U32
+    w = ((A ^ C) & 0x00010001) & va & vc
+    rep = lambda h: h | (h << 16)
+    return hfma2((va + vc + 2 * w) & U32, rep(H_QUARTER_LO), 0)
+
+
+def test_fp16_decode_predictor_matches_reference():
+    for m in range(0, 1023):
+        assert hfma_lane(m, H_QUARTER_LO, 0) == (m + 1) // 4, m
+    rng = np.random.default_rng(12)
+    for v in rng.integers(0, 256, (20000, 8)):
+        A, B, C, D, A2, B2, C2, D2 = (int(x) for x in v)
+        args = (A | (A2 << 16), B | (B2 << 16), C | (C2 << 16), D | (D2 << 16))
+        got = fp16_pred(*args)
+        assert (got & 0xFFFF, got >> 16) == (ref_pred(A, B, C, D), ref_pred(A2, B2, C2, D2)) and got == swar_pred(*args)
 
 
 def test_fp16_predictor_matches_reference():
