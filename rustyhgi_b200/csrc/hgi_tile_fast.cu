@@ -110,7 +110,13 @@ __device__ __forceinline__ void store_chunk(uint8_t* __restrict__ ptr, const uin
 {
     if (nvalid <= 0) return;
     if (ALIGNED) {
+#if defined(HGI_VAR_STCS)
+        __stcs(reinterpret_cast<uint4*>(ptr), make_uint4(w[0], w[1], w[2], w[3]));   // streaming (evict-first) store, A/B hook
+#elif defined(HGI_VAR_STCG)
+        __stcg(reinterpret_cast<uint4*>(ptr), make_uint4(w[0], w[1], w[2], w[3]));
+#else
         *reinterpret_cast<uint4*>(ptr) = make_uint4(w[0], w[1], w[2], w[3]);
+#endif
         return;
     }
     const uint32_t sh = (uint32_t)((uintptr_t)ptr & 3u);
@@ -207,6 +213,15 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     // warps skip the block with one uniform branch (1.266 / 1.722 / 1.242): the identity encode takes the second.
     constexpr bool HALO_WARP = (MODE == kModeEncode) && IDENTITY;
     constexpr int NRIGHT = TH / 2, NHALO = NRIGHT + 27, NRL = NRIGHT / 32;
+    // HGI_VAR_HALO_TWO_WARPS / _DECODE: whole warps fetch the halo (warp 1 the right column, warp 2 the bottom rows), A/B
+    // hook: encode Medium +1 % slower, decode -0.8 % (inside the noise) -- not the default
+#if defined(HGI_VAR_HALO_TWO_WARPS_DECODE)
+    constexpr bool HALO_TWO_WARPS = (TH == 64 && NT == 128);
+#elif defined(HGI_VAR_HALO_TWO_WARPS)
+    constexpr bool HALO_TWO_WARPS = (TH == 64 && NT == 128) && !(MODE == kModeDecode);
+#else
+    constexpr bool HALO_TWO_WARPS = false;
+#endif
     // -- spread form
     const int hj = tid - (NT - (TH == 64 ? 64 : 128));
     int hy = 2 * hj, hc = 8;
@@ -220,7 +235,23 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     for (int k = 0; k < NRL; ++k) hvr[k] = make_uint4(0u, 0u, 0u, 0u);
     int hyb = TH, hcb = 0;
     bool has_b = false;
-    if (!HALO_WARP) {
+    if (!HALO_WARP && HALO_TWO_WARPS) {
+        // warp 1: the 32 right-halo chunks, one per lane; warp 2: the 27 bottom chunks.  Whole warps, so the others skip
+        // the address arithmetic with a uniform branch (the spread form below is if-converted: every warp issues it),
+        // and warps 1 and 2 are the ones with the least other work (warp 0 runs the s = 8 level, warp 3 the s = 2 fringe).
+        const int wid = tid >> 5, lane = tid & 31;
+        if (NLEV > 1 && wid == 1) {
+            hy = 2 * lane;
+            halo = true;
+            if (hy < yin) hv = load_chunk<ALIGNED>(tile + (uint32_t)hy * p.pitch + (uint32_t)TW, min(16, xin - TW), false, ragged);
+        } else if (NLEV > 1 && wid == 2 && lane < 27) {
+            const int r = (lane >= 9) + (lane >= 18);
+            hc = lane - 9 * r;
+            hy = TH + 4 * r;
+            halo = true;
+            if (hy < yin) hv = load_chunk<ALIGNED>(tile + (uint32_t)hy * p.pitch + (uint32_t)(16 * hc), min(16, xin - 16 * hc), false, ragged);
+        }
+    } else if (!HALO_WARP) {
         if (hj >= NRIGHT) {
             const int r = (hj - NRIGHT) / 9;
             hc = (hj - NRIGHT) - 9 * r;

@@ -401,9 +401,11 @@ __device__ __forceinline__ void level_word(FastSmem& sm, int g, int cy, const Qu
     uint8_t* Ps = sm.P + plane_off(S);
     const uint8_t* Pc = sm.P + plane_off(2 * S);
     const uint8_t* ct = Pc + cy * pc + 2 * g;
-    const uint32_t cwt = (uint32_t)*reinterpret_cast<const uint16_t*>(ct) | ((uint32_t)ct[2] << 16);
-    const uint32_t cwb = (uint32_t)*reinterpret_cast<const uint16_t*>(ct + pc) | ((uint32_t)ct[pc + 2] << 16);
-    const uint32_t A = lanes01(cwt), C = lanes12(cwt), B = lanes01(cwb), D = lanes12(cwb);
+    // three corner bytes per row as a 16-bit and an 8-bit load (zero-extended): their zero bytes serve as the lane
+    // padding, so the two registers need not be merged first
+    const uint32_t tlo = *reinterpret_cast<const uint16_t*>(ct), thi = ct[2];
+    const uint32_t blo = *reinterpret_cast<const uint16_t*>(ct + pc), bhi = ct[pc + 2];
+    const uint32_t A = prmt(tlo, thi, 0x3120u), C = prmt(tlo, thi, 0x3421u), B = prmt(blo, bhi, 0x3120u), D = prmt(blo, bhi, 0x3421u);
     uint32_t* pev = reinterpret_cast<uint32_t*>(Ps + (2 * cy) * ps + 4 * g);
     uint32_t* pod = reinterpret_cast<uint32_t*>(Ps + (2 * cy + 1) * ps + 4 * g);
     const uint32_t ev = *pev, od = *pod;
@@ -501,9 +503,11 @@ __device__ __forceinline__ void fringe2_word(FastSmem& sm, int it, const QuantSw
     const bool is_row = it < wpr;
     const int g = is_row ? it : wpr, cy = is_row ? ncy : it - wpr;
     const uint8_t* ct = sm.P + plane_off(4) + cy * pc + 2 * g;
-    const uint32_t cwt = (uint32_t)*reinterpret_cast<const uint16_t*>(ct) | ((uint32_t)ct[2] << 16);
-    const uint32_t cwb = (uint32_t)*reinterpret_cast<const uint16_t*>(ct + pc) | ((uint32_t)ct[pc + 2] << 16);
-    const uint32_t A = lanes01(cwt), C = lanes12(cwt), B = lanes01(cwb), D = lanes12(cwb);
+    // three corner bytes per row as a 16-bit and an 8-bit load (zero-extended): their zero bytes serve as the lane
+    // padding, so the two registers need not be merged first
+    const uint32_t tlo = *reinterpret_cast<const uint16_t*>(ct), thi = ct[2];
+    const uint32_t blo = *reinterpret_cast<const uint16_t*>(ct + pc), bhi = ct[pc + 2];
+    const uint32_t A = prmt(tlo, thi, 0x3120u), C = prmt(tlo, thi, 0x3421u), B = prmt(blo, bhi, 0x3120u), D = prmt(blo, bhi, 0x3421u);
     uint8_t* ev = sm.P + plane_off(2) + (2 * cy) * ps + 4 * g;
     const uint32_t w = *reinterpret_cast<const uint32_t*>(is_row ? ev : ev + ps);
     const uint32_t a = prmt(w, 0u, is_row ? 0x4341u : 0x4240u);
