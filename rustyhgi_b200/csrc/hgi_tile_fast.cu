@@ -45,6 +45,7 @@
 #ifdef HGI_FAST_NT
 #define HGI_TILE_NT HGI_FAST_NT
 #endif
+#include <cstdlib>
 #include "hgi_tile_swar.cuh"
 
 namespace hgi {
@@ -204,6 +205,14 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
         const bool last1 = EDGE != 0 && (img + 1 == gridDim.z) && (Y0 + (uint32_t)y + 2 >= p.h) && (X0 + 16u * sx + 16u >= p.pitch);
         ev[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * u) * p.pitch, y < yin ? nvalid : 0, !last0, ragged);
         od[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * u + 1) * p.pitch, y + 1 < yin ? nvalid : 0, !last1, ragged);
+    }
+
+    // L2 prefetch for a CTA that starts about one residency later: the same tile `pf_images` planes ahead (batches) or the
+    // tile `pf_rows` tile rows further down (large planes; split launches only, where every target row is interior).
+    // One 128-byte line per tile row.
+    if (EDGE == 0 && p.pf_off != 0u && img + p.pf_images < gridDim.z && ty + p.pf_rows < gridDim.y && tid < TH) {
+        const uint8_t* pf = tile + p.pf_off + (uint32_t)tid * p.pitch;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
     }
 
     // halo chunks (right of / below the tile) feed only the coarse planes: TH/2 right-halo chunks (rows 0,2,..,TH-2;
@@ -539,8 +548,27 @@ cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
     if (tiles_x == 0 || tiles_y == 0 || args.n_images == 0) return cudaSuccess;
     if (tiles_y > 65535u) return cudaErrorInvalidConfiguration;
     const size_t plane = (size_t)args.pitch * args.h;
+    // L2 prefetch distance of the interior tiles, in residencies (148 SMs x 10 CTAs): the quantizing encode is bound by
+    // its instruction stream, so the DRAM latency of a tile's first loads is the one stall it cannot cover with other
+    // work; fetching the tile into L2 one to two residencies earlier costs nothing (-3 %, A/B).  The light kernels are
+    // DRAM-bound: any distance beyond a residency makes them re-read evicted lines (+20 % at k = 2), so theirs is off.
+    // HGI_B200_PREFETCH=<k> / HGI_B200_PREFETCH_LIGHT=<k> override (0 = off).
+    static const double pf_kq = [] { const char* e = getenv("HGI_B200_PREFETCH"); return e ? atof(e) : 1.0; }();
+    static const double pf_kl = [] { const char* e = getenv("HGI_B200_PREFETCH_LIGHT"); return e ? atof(e) : 0.0; }();
+    const bool quantizing = (MODE == kModeEncode && args.quant_error != 0);
+    const double pf_tiles = (quantizing ? pf_kq : pf_kl) * 1480.0;
+    const uint64_t tiles_img = (uint64_t)tiles_x * tiles_y;
+    uint32_t pf_images = 0, pf_rows = 0;
+    if (pf_tiles > 0.0) {
+        if ((double)tiles_img <= pf_tiles) pf_images = (uint32_t)((pf_tiles + (double)tiles_img - 1.0) / (double)tiles_img);
+        else if (quantizing && ALIGNED && NLEV == 4 && tiles_img * args.n_images >= kSplitMinTiles)   // the split launch: rows of interior tiles
+            pf_rows = (uint32_t)((pf_tiles + (double)tiles_x - 1.0) / (double)tiles_x);
+    }
     for (uint32_t first = 0; first < args.n_images; first += 65535u) {   // gridDim.z limit
         PassArgs a = args;
+        a.pf_images = pf_images;
+        a.pf_rows = pf_rows;
+        a.pf_off = ((uint64_t)pf_images * args.h + (uint64_t)pf_rows * TH) * args.pitch;
         a.n_images = args.n_images - first < 65535u ? args.n_images - first : 65535u;
         a.src = args.src + (size_t)first * plane;
         if (args.grid_out) a.grid_out = args.grid_out + (size_t)first * plane;

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A/B harness for kernel variants: runs bench.py (device-resident leg only) with each library given on the command
 line, interleaved ABAB... on the same box so that box-to-box and thermal drift cancel, and prints the median
-per-kernel milliseconds.    python tools/ab_bench.py [--rounds 3] [--frames 2048] name=path.so ..."""
+per-kernel milliseconds.    python tools/ab_bench.py [--rounds 3] [--frames 2048] name=path.so[,ENV=VALUE...] ..."""
 import argparse
 import json
 import os
@@ -23,7 +23,8 @@ def main():
     res = {n: [] for n, _ in libs}
     for _ in range(a.rounds):
         for name, path in libs:
-            env = dict(os.environ, HGI_B200_LIB=os.path.abspath(path))
+            path, *extra = path.split(",")
+            env = dict(os.environ, HGI_B200_LIB=os.path.abspath(path), **dict(e.split("=", 1) for e in extra))
             out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(a.steps), "--no-cpu", "--no-e2e",
                                   "--frames", str(a.frames)], env=env, capture_output=True, text=True)
             line = [l for l in out.stdout.splitlines() if l.startswith("{")]
