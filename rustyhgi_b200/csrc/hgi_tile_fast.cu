@@ -210,6 +210,7 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     // L2 prefetch for a CTA that starts about one residency later: the same tile `pf_images` planes ahead (batches) or the
     // tile `pf_rows` tile rows further down (large planes; split launches only, where every target row is interior).
     // One 128-byte line per tile row.
+    // (also prefetching the halo rows TH, TH+4, TH+8, TH+16 measured no gain: the neighbours' own prefetches cover them)
     if (EDGE == 0 && p.pf_off != 0u && img + p.pf_images < gridDim.z && ty + p.pf_rows < gridDim.y && tid < TH) {
         const uint8_t* pf = tile + p.pf_off + (uint32_t)tid * p.pitch;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
