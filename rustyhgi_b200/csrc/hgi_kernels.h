@@ -34,10 +34,11 @@ struct PassArgs {
     uint32_t tiles_x, tiles_y;
     uint32_t fast_tx, fast_itx, fast_ity;   // fast tile kernel, split launch: tiles per row, interior tile columns / rows
     uint32_t n_images;
-    // fast kernel, interior tiles: L2 prefetch of the tile `pf_images` planes or `pf_rows` tile rows ahead (one of the two;
-    // both 0 = off); pf_off = the byte distance
-    uint32_t pf_images, pf_rows;
-    uint64_t pf_off;
+    // fast kernel, quantizing encode, interior tiles: L2 prefetch of the tile at pf_src = src + distance (the same tile of a later
+    // plane, or a tile some tile rows further down a large plane) by the CTAs with image index < pf_zlim and tile row
+    // < pf_ylim (the launcher's bounds for "the target tile exists and is interior"; pf_zlim = 0: off)
+    uint32_t pf_zlim, pf_ylim;
+    const uint8_t* pf_src;
     uint32_t quant_error;    // 0 => identity quantizer
     uint32_t vec_ok;         // rows and bases are 16-byte aligned => 128-bit global accesses (1: rows are whole chunks, 2: padded rows)
     // SWAR quantizer constants (quant_swar() of hgi_tile_swar.cuh, evaluated on the host per launch)

@@ -207,13 +207,14 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
         od[u] = load_chunk<ALIGNED>(tile + toff + (uint32_t)(2 * u + 1) * p.pitch, y + 1 < yin ? nvalid : 0, !last1, ragged);
     }
 
-    // L2 prefetch for a CTA that starts about one residency later: the same tile `pf_images` planes ahead (batches) or the
-    // tile `pf_rows` tile rows further down (large planes; split launches only, where every target row is interior).
-    // One 128-byte line per tile row.
-    // (also prefetching the halo rows TH, TH+4, TH+8, TH+16 measured no gain: the neighbours' own prefetches cover them)
-    if (EDGE == 0 && p.pf_off != 0u && img + p.pf_images < gridDim.z && ty + p.pf_rows < gridDim.y && tid < TH) {
-        const uint8_t* pf = tile + p.pf_off + (uint32_t)tid * p.pitch;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+    // L2 prefetch for a CTA that starts about one residency later (quantizing encode only, see launch_fast_n): one
+    // 128-byte line per tile row.  The bounds are CTA-uniform and evaluated by the launcher, so the other kernels and
+    // the edge bodies carry nothing.  (Also prefetching the halo rows TH, TH+4, TH+8, TH+16 measured no gain.)
+    if (EDGE == 0 && MODE == kModeEncode && !IDENTITY && img < p.pf_zlim && ty < p.pf_ylim) {
+        if (tid < TH) {
+            const uint8_t* pf = p.pf_src + tile_off + (uint32_t)tid * p.pitch;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+        }
     }
 
     // halo chunks (right of / below the tile) feed only the coarse planes: TH/2 right-halo chunks (rows 0,2,..,TH-2;
@@ -549,29 +550,30 @@ cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
     if (tiles_x == 0 || tiles_y == 0 || args.n_images == 0) return cudaSuccess;
     if (tiles_y > 65535u) return cudaErrorInvalidConfiguration;
     const size_t plane = (size_t)args.pitch * args.h;
-    // L2 prefetch distance of the interior tiles, in residencies (148 SMs x 10 CTAs): the quantizing encode is bound by
-    // its instruction stream, so the DRAM latency of a tile's first loads is the one stall it cannot cover with other
-    // work; fetching the tile into L2 one to two residencies earlier costs nothing (-3 %, A/B).  The light kernels are
-    // DRAM-bound: any distance beyond a residency makes them re-read evicted lines (+20 % at k = 2), so theirs is off.
-    // HGI_B200_PREFETCH=<k> / HGI_B200_PREFETCH_LIGHT=<k> override (0 = off).
-    static const double pf_kq = [] { const char* e = getenv("HGI_B200_PREFETCH"); return e ? atof(e) : 1.0; }();
-    static const double pf_kl = [] { const char* e = getenv("HGI_B200_PREFETCH_LIGHT"); return e ? atof(e) : 0.0; }();
-    const bool quantizing = (MODE == kModeEncode && args.quant_error != 0);
-    const double pf_tiles = (quantizing ? pf_kq : pf_kl) * 1480.0;
+    // L2 prefetch distance of the interior tiles of the quantizing encode, in residencies (148 SMs x 10 CTAs): that
+    // kernel is bound by its instruction stream, so the DRAM latency of a tile's first loads is the one stall it cannot
+    // cover with other work; fetching the tile into L2 about one residency earlier takes it away (-2..3 %, A/B sweep:
+    // k = 0.5..2 alike, beyond k = 2.5 the lines are evicted before use and the kernel loses 8 %).  The DRAM-bound light
+    // kernels lose with any distance (+20 % at k = 2) and do not carry the code.  HGI_B200_PREFETCH=<k> overrides, 0 = off.
+    static const double pf_k = [] { const char* e = getenv("HGI_B200_PREFETCH"); return e ? atof(e) : 1.0; }();
+    const bool split = (MODE == kModeEncode && args.quant_error != 0 && ALIGNED && NLEV == 4 &&
+                        (uint64_t)tiles_x * tiles_y * args.n_images >= kSplitMinTiles);   // only the split launch has interior-only CTAs
+    const double pf_tiles = split ? pf_k * 1480.0 : 0.0;
     const uint64_t tiles_img = (uint64_t)tiles_x * tiles_y;
     uint32_t pf_images = 0, pf_rows = 0;
     if (pf_tiles > 0.0) {
         if ((double)tiles_img <= pf_tiles) pf_images = (uint32_t)((pf_tiles + (double)tiles_img - 1.0) / (double)tiles_img);
-        else if (quantizing && ALIGNED && NLEV == 4 && tiles_img * args.n_images >= kSplitMinTiles)   // the split launch: rows of interior tiles
-            pf_rows = (uint32_t)((pf_tiles + (double)tiles_x - 1.0) / (double)tiles_x);
+        else pf_rows = (uint32_t)((pf_tiles + (double)tiles_x - 1.0) / (double)tiles_x);
     }
     for (uint32_t first = 0; first < args.n_images; first += 65535u) {   // gridDim.z limit
         PassArgs a = args;
-        a.pf_images = pf_images;
-        a.pf_rows = pf_rows;
-        a.pf_off = ((uint64_t)pf_images * args.h + (uint64_t)pf_rows * TH) * args.pitch;
         a.n_images = args.n_images - first < 65535u ? args.n_images - first : 65535u;
         a.src = args.src + (size_t)first * plane;
+        // bounds against this launch's grid: planes [0, n - pf_images) / interior tile rows [0, fast_ity - pf_rows)
+        const uint32_t ity = a.h >= (uint32_t)(FMAX + 1) ? min(tiles_y, (a.h - (FMAX + 1)) / TH) : 0u;
+        a.pf_zlim = pf_images ? (a.n_images > pf_images ? a.n_images - pf_images : 0u) : (pf_rows ? a.n_images : 0u);
+        a.pf_ylim = pf_rows ? (ity > pf_rows ? ity - pf_rows : 0u) : 0xFFFFFFFFu;
+        a.pf_src = a.src + ((uint64_t)pf_images * args.h + (uint64_t)pf_rows * TH) * args.pitch;
         if (args.grid_out) a.grid_out = args.grid_out + (size_t)first * plane;
         if (args.recon_out) a.recon_out = args.recon_out + (size_t)first * plane;
         if (args.c_recon) a.c_recon = args.c_recon + (size_t)first * args.cpitch * args.ch;
