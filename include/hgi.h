@@ -102,7 +102,9 @@ void hgi_ctx_destroy(hgi_ctx_t *ctx);
 int hgi_ctx_set_path(hgi_ctx_t *ctx, int path /* hgi_path_t */);
 /* Host-pointer entry points stream a batch through `slots` (1..4) stream slots in chunks of `chunk_mb` MiB (H2D,
    kernels and D2H of different chunks overlap).  0 = the default (64 MiB, 3 slots; HGI_B200_CHUNK_MB and
-   HGI_B200_SLOTS in the environment override the default). */
+   HGI_B200_SLOTS in the environment override the default).  A non-zero `chunk_mb` is also the chunk of
+   hgi_histogram_u8 / hgi_error_metrics_u8 (MiB) and hgi_rgb_to_luma_u8 (Mi pixels), which alternate their chunks
+   between two slots (defaults: 1024 / 256 MiB / 64 Mi pixels). */
 int hgi_ctx_set_pipeline(hgi_ctx_t *ctx, uint32_t chunk_mb, uint32_t slots);
 int hgi_ctx_synchronize(hgi_ctx_t *ctx);
 /* cudaError_t of the last failing runtime call (0 if none) and its string. */

@@ -554,6 +554,33 @@ int run_dev_cached(hgi_ctx* ctx, Scratch& sc, int mode, const uint8_t* src, uint
 // bytes; the per-image residual histogram has 32-bit bins.
 constexpr uint32_t kMaxPitch = 1u << 26;
 
+// Two-slot pipeline of the reductions / colour conversion over host buffers (hgi_histogram_u8, hgi_error_metrics_u8,
+// hgi_rgb_to_luma_u8): streams and staging buffers of slots 0..ns-1; every stream is drained before the call returns,
+// on the error path too (the D2H copies target caller memory).
+int cuda_rc(hgi_ctx* ctx, cudaError_t e) { return e == cudaSuccess ? HGI_OK : fail(ctx, e); }
+
+int two_slots(hgi_ctx* ctx, int ns, size_t in_bytes, size_t out_bytes)
+{
+    for (int k = 0; k < ns; ++k) {
+        Slot& sl = ctx->slots[k];
+        if (!sl.stream) HGI_CUDA(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        int rc = reserve(ctx, sl.in, in_bytes);
+        if (!rc && out_bytes) rc = reserve(ctx, sl.out, out_bytes);
+        if (rc) return rc;
+    }
+    return HGI_OK;
+}
+
+int drain_two(hgi_ctx* ctx, int ns, int rc)
+{
+    for (int k = 0; k < ns; ++k)
+        if (ctx->slots[k].stream) {
+            const cudaError_t e = cudaStreamSynchronize(ctx->slots[k].stream);
+            if (e != cudaSuccess && rc == HGI_OK) rc = fail(ctx, e);
+        }
+    return rc;
+}
+
 bool plane_size_ok(uint32_t w, uint32_t h, uint32_t n_images, uint32_t pitch = 0)
 {
     if (pitch == 0) pitch = w;
@@ -669,7 +696,7 @@ int hgi_ctx_create(int device, hgi_ctx_t** ctx_out)
     ctx->device = device;
     DeviceGuard g(ctx);
     cudaError_t e = g.ok ? cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) : ctx->last_err;
-    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_metrics, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_metrics, 4 * sizeof(unsigned long long))   /* two per pipeline slot */;
     if (e != cudaSuccess) {
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         delete ctx;
@@ -930,21 +957,23 @@ int hgi_rgb_to_luma_u8(hgi_ctx_t* ctx, const uint8_t* rgb, size_t n_pixels, uint
     if (!rgb || !luma_out || n_pixels > ((size_t)1 << 60)) return HGI_ERR_INVALID_ARG;
     DeviceGuard g(ctx);
     if (!g.ok) return HGI_ERR_CUDA;
-    Slot& sl = ctx->slots[0];
-    if (!sl.stream) HGI_CUDA(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-    const size_t chunk = (size_t)64 << 20;   // pixels per chunk
-    int rc = reserve(ctx, sl.in, 3 * (n_pixels < chunk ? n_pixels : chunk));
-    if (!rc) rc = reserve(ctx, sl.out, n_pixels < chunk ? n_pixels : chunk);
+    // chunks alternate between two slots: the H2D copy of chunk i+1 overlaps the kernel and the D2H copy of chunk i
+    const size_t chunk = ctx->chunk_bytes ? ctx->chunk_bytes : ((size_t)64 << 20);   // pixels per chunk
+    const size_t cap = n_pixels < chunk ? n_pixels : chunk;
+    const int ns = n_pixels > chunk ? 2 : 1;
+    int rc = two_slots(ctx, ns, 3 * cap, cap);
     if (rc) return rc;
-    for (size_t off = 0; off < n_pixels; off += chunk) {
+    size_t i = 0;
+    for (size_t off = 0; off < n_pixels && !rc; off += chunk, ++i) {
+        Slot& sl = ctx->slots[i & 1];
         const size_t len = (n_pixels - off < chunk) ? n_pixels - off : chunk;
-        HGI_CUDA(ctx, cudaMemcpyAsync(sl.in.p, rgb + 3 * off, 3 * len, cudaMemcpyHostToDevice, sl.stream));
-        HGI_CUDA(ctx, hgi::launch_rgb_to_luma(sl.in.p, len, sl.out.p, sl.stream));
-        ctx->launches++;
-        HGI_CUDA(ctx, cudaMemcpyAsync(luma_out + off, sl.out.p, len, cudaMemcpyDeviceToHost, sl.stream));
-        HGI_CUDA(ctx, cudaStreamSynchronize(sl.stream));
+        if (i >= 2) rc = cuda_rc(ctx, cudaStreamSynchronize(sl.stream));
+        if (!rc) rc = cuda_rc(ctx, cudaMemcpyAsync(sl.in.p, rgb + 3 * off, 3 * len, cudaMemcpyHostToDevice, sl.stream));
+        if (!rc) rc = cuda_rc(ctx, hgi::launch_rgb_to_luma(sl.in.p, len, sl.out.p, sl.stream));
+        if (!rc) ctx->launches++;
+        if (!rc) rc = cuda_rc(ctx, cudaMemcpyAsync(luma_out + off, sl.out.p, len, cudaMemcpyDeviceToHost, sl.stream));
     }
-    return HGI_OK;
+    return drain_two(ctx, ns, rc);
 }
 
 int hgi_encode_batch_u8(hgi_ctx_t* ctx, const uint8_t* images, uint32_t n_images, uint32_t width, uint32_t height,
@@ -1003,29 +1032,46 @@ int hgi_histogram_u8(hgi_ctx_t* ctx, const uint8_t* grid, size_t n, uint64_t his
     if (!grid) return HGI_ERR_INVALID_ARG;
     DeviceGuard g(ctx);
     if (!g.ok) return HGI_ERR_CUDA;
-    Slot& sl = ctx->slots[0];
-    if (!sl.stream) HGI_CUDA(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-    const size_t chunk = (size_t)1 << 30;  // keeps the u32 device bins far from overflow (and the length a uint32_t)
-    int rc = reserve(ctx, sl.in, n < chunk ? n : chunk);
+    // keeps the u32 device bins far from overflow (and the length a uint32_t); two slots as in hgi_rgb_to_luma_u8
+    const size_t chunk = ctx->chunk_bytes ? ctx->chunk_bytes : ((size_t)1 << 30);
+    const int ns = n > chunk ? 2 : 1;
+    int rc = two_slots(ctx, ns, n < chunk ? n : chunk, 0);
+    for (int k = 0; k < ns && !rc; ++k) {
+        Slot& sl = ctx->slots[k];
+        if (sl.hist_cap < 256) {
+            if (sl.hist) rc = cuda_rc(ctx, cudaFree(sl.hist));
+            sl.hist = nullptr;
+            sl.hist_cap = 0;
+            if (!rc) rc = cuda_rc(ctx, cudaMalloc((void**)&sl.hist, 256 * sizeof(uint32_t)));
+            if (!rc) sl.hist_cap = 256;
+        }
+    }
     if (rc) return rc;
-    if (sl.hist_cap < 256) {
-        if (sl.hist) HGI_CUDA(ctx, cudaFree(sl.hist));
-        sl.hist = nullptr;
-        sl.hist_cap = 0;
-        HGI_CUDA(ctx, cudaMalloc((void**)&sl.hist, 256 * sizeof(uint32_t)));
-        sl.hist_cap = 256;
-    }
-    uint32_t part[256];
-    for (size_t off = 0; off < n; off += chunk) {
+    uint32_t part[2][256];
+    bool pending[2] = {false, false};
+    size_t i = 0;
+    for (size_t off = 0; off < n && !rc; off += chunk, ++i) {
+        const int k = (int)(i & 1);
+        Slot& sl = ctx->slots[k];
         const size_t len = (n - off < chunk) ? n - off : chunk;
-        HGI_CUDA(ctx, cudaMemcpyAsync(sl.in.p, grid + off, len, cudaMemcpyHostToDevice, sl.stream));
-        HGI_CUDA(ctx, hgi::launch_histogram(sl.in.p, (uint32_t)len, 1u, (uint32_t)len, 1, sl.hist, sl.stream));
-        ctx->launches++;
-        HGI_CUDA(ctx, cudaMemcpyAsync(part, sl.hist, sizeof(part), cudaMemcpyDeviceToHost, sl.stream));
-        HGI_CUDA(ctx, cudaStreamSynchronize(sl.stream));
-        for (int i = 0; i < 256; ++i) hist_out[i] += part[i];
+        if (pending[k]) {
+            rc = cuda_rc(ctx, cudaStreamSynchronize(sl.stream));
+            if (rc) break;
+            for (int b = 0; b < 256; ++b) hist_out[b] += part[k][b];
+            pending[k] = false;
+        }
+        rc = cuda_rc(ctx, cudaMemcpyAsync(sl.in.p, grid + off, len, cudaMemcpyHostToDevice, sl.stream));
+        if (!rc) rc = cuda_rc(ctx, hgi::launch_histogram(sl.in.p, (uint32_t)len, 1u, (uint32_t)len, 1, sl.hist, sl.stream));
+        if (!rc) ctx->launches++;
+        if (!rc) rc = cuda_rc(ctx, cudaMemcpyAsync(part[k], sl.hist, sizeof(part[k]), cudaMemcpyDeviceToHost, sl.stream));
+        if (!rc) pending[k] = true;
     }
-    return HGI_OK;
+    rc = drain_two(ctx, ns, rc);
+    if (!rc)
+        for (int k = 0; k < 2; ++k)
+            if (pending[k])
+                for (int b = 0; b < 256; ++b) hist_out[b] += part[k][b];
+    return rc;
 }
 
 int hgi_error_metrics_u8(hgi_ctx_t* ctx, const uint8_t* before, const uint8_t* after, size_t n,
@@ -1037,24 +1083,39 @@ int hgi_error_metrics_u8(hgi_ctx_t* ctx, const uint8_t* before, const uint8_t* a
     if (n) {
         DeviceGuard g(ctx);
         if (!g.ok) return HGI_ERR_CUDA;
-        Slot& sl = ctx->slots[0];
-        if (!sl.stream) HGI_CUDA(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-        const size_t chunk = (size_t)256 << 20;
-        int rc = reserve(ctx, sl.in, n < chunk ? n : chunk);
-        if (!rc) rc = reserve(ctx, sl.out, n < chunk ? n : chunk);
+        const size_t chunk = ctx->chunk_bytes ? ctx->chunk_bytes : ((size_t)256 << 20);   // two slots as in hgi_rgb_to_luma_u8
+        const size_t cap = n < chunk ? n : chunk;
+        const int ns = n > chunk ? 2 : 1;
+        int rc = two_slots(ctx, ns, cap, cap);
         if (rc) return rc;
-        for (size_t off = 0; off < n; off += chunk) {
+        unsigned long long part[2][2];
+        bool pending[2] = {false, false};
+        size_t i = 0;
+        for (size_t off = 0; off < n && !rc; off += chunk, ++i) {
+            const int k = (int)(i & 1);
+            Slot& sl = ctx->slots[k];
             const size_t len = (n - off < chunk) ? n - off : chunk;
-            unsigned long long part[2];
-            HGI_CUDA(ctx, cudaMemcpyAsync(sl.in.p, before + off, len, cudaMemcpyHostToDevice, sl.stream));
-            HGI_CUDA(ctx, cudaMemcpyAsync(sl.out.p, after + off, len, cudaMemcpyHostToDevice, sl.stream));
-            HGI_CUDA(ctx, hgi::launch_error_metrics(sl.in.p, sl.out.p, len, ctx->d_metrics, sl.stream));
-            ctx->launches++;
-            HGI_CUDA(ctx, cudaMemcpyAsync(part, ctx->d_metrics, sizeof(part), cudaMemcpyDeviceToHost, sl.stream));
-            HGI_CUDA(ctx, cudaStreamSynchronize(sl.stream));
-            total += part[0];
-            if (part[1] > mx) mx = part[1];
+            if (pending[k]) {
+                rc = cuda_rc(ctx, cudaStreamSynchronize(sl.stream));
+                if (rc) break;
+                total += part[k][0];
+                if (part[k][1] > mx) mx = part[k][1];
+                pending[k] = false;
+            }
+            rc = cuda_rc(ctx, cudaMemcpyAsync(sl.in.p, before + off, len, cudaMemcpyHostToDevice, sl.stream));
+            if (!rc) rc = cuda_rc(ctx, cudaMemcpyAsync(sl.out.p, after + off, len, cudaMemcpyHostToDevice, sl.stream));
+            if (!rc) rc = cuda_rc(ctx, hgi::launch_error_metrics(sl.in.p, sl.out.p, len, ctx->d_metrics + 2 * k, sl.stream));
+            if (!rc) ctx->launches++;
+            if (!rc) rc = cuda_rc(ctx, cudaMemcpyAsync(part[k], ctx->d_metrics + 2 * k, sizeof(part[k]), cudaMemcpyDeviceToHost, sl.stream));
+            if (!rc) pending[k] = true;
         }
+        rc = drain_two(ctx, ns, rc);
+        if (rc) return rc;
+        for (int k = 0; k < 2; ++k)
+            if (pending[k]) {
+                total += part[k][0];
+                if (part[k][1] > mx) mx = part[k][1];
+            }
     }
     if (sum_sq_out) *sum_sq_out = total;
     if (sd_int_out) *sd_int_out = n ? total / n : 0;  // src/main.rs:106 integer division

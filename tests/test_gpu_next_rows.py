@@ -128,3 +128,23 @@ def test_cli_encode_decode_roundtrip(tmp_path):
 def test_cli_swallows_errors_like_reference(tmp_path, capsys):
     cli.main(["decode", "-i", str(tmp_path / "missing.hgi"), "-o", str(tmp_path / "x.png")])
     assert "An error occured" in capsys.readouterr().err               # src/main.rs:130-134
+
+
+def test_host_reductions_in_many_chunks():
+    """hgi_histogram_u8 / hgi_error_metrics_u8 / hgi_rgb_to_luma_u8 cut their input into chunks that alternate between
+    two pipeline slots; with 1 MB chunks a 5.3 MB input is six of them (odd count, ragged tail)."""
+    ctx = hgi.Context()
+    ctx.check(hgi.lib().hgi_ctx_set_pipeline(ctx._h, 1, 0), "hgi_ctx_set_pipeline")
+    rng = np.random.default_rng(9)
+    n = 5 * (1 << 20) + 333_333
+    a = rng.integers(0, 256, n).astype(np.uint8)
+    b = np.clip(a.astype(np.int16) + rng.integers(-9, 10, n), 0, 255).astype(np.uint8)
+    assert (hgi.histogram(a, ctx=ctx) == np.bincount(a, minlength=256)).all()
+    diff = a.astype(np.int64) - b.astype(np.int64)
+    m = hgi.error_metrics(a, b, ctx=ctx)
+    assert m["sum_sq"] == int((diff * diff).sum()) and m["max_abs"] == int(np.abs(diff).max())
+    rgb = rng.integers(0, 256, (1, n // 3, 3)).astype(np.uint8)      # 1.78 M pixels: two chunks of 1 M pixels
+    assert (hgi.rgb_to_luma(rgb, ctx=ctx) == oc.rgb_to_luma(rgb)).all()
+    for rep in range(3):                                               # slots are reused across calls
+        assert (hgi.histogram(b, ctx=ctx) == np.bincount(b, minlength=256)).all()
+    ctx.close()
