@@ -501,7 +501,13 @@ hgi_tile_fast_part_kernel(const PassArgs p)
 }
 
 // below this many tiles (about four waves of 10 CTAs on 148 SMs) the second launch costs more than the edge predicates
-constexpr uint64_t kSplitMinTiles = 4 * 1480;
+// (HGI_B200_SPLIT_MIN=<tiles> overrides, a tuning hook)
+inline uint64_t split_min_tiles()
+{
+    static const uint64_t v = [] { const char* e = getenv("HGI_B200_SPLIT_MIN"); return e ? (uint64_t)atoll(e) : (uint64_t)(4 * 1480); }();
+    return v;
+}
+#define kSplitMinTiles split_min_tiles()
 
 template <int MODE, int INTERP, bool EXTRA, int NLEV, bool ALIGNED>
 cudaError_t launch_fast_split(PassArgs& a, uint32_t tiles_x, uint32_t tiles_y, cudaStream_t stream)

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--levels", type=int, default=8)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--one-band-of", type=int, default=0, help="single GPU: time band 0 of an N-band plan (what one rank of N does)")
     a = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -38,7 +39,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     n, L = a.size, a.levels
-    bands = sharding.plan_bands(n, L, world)
+    bands = sharding.plan_bands(n, L, a.one_band_of if a.one_band_of else world)
     b = bands[rank] if rank < len(bands) else None
     ctx = hgi.Context(local)
     enc = hgi.Encoder(hgi.Crossed, hgi.Linear(hgi.QuantizationLevel.Medium), L, ctx=ctx)
