@@ -509,7 +509,7 @@ inline uint64_t split_min_tiles()
 }
 #define kSplitMinTiles split_min_tiles()
 
-template <int MODE, int INTERP, bool EXTRA, int NLEV, bool ALIGNED>
+template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED>
 cudaError_t launch_fast_split(PassArgs& a, uint32_t tiles_x, uint32_t tiles_y, cudaStream_t stream)
 {
     a.fast_tx = tiles_x;
@@ -526,20 +526,20 @@ cudaError_t launch_fast_split(PassArgs& a, uint32_t tiles_x, uint32_t tiles_y, c
     }
     if (a.fast_itx) {
         const dim3 nb(a.fast_itx, a.fast_ity, a.n_images);
-        hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 1><<<nb, NT, 0, stream>>>(a); ++launch_count();
+        hgi_tile_fast_part_kernel<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 1><<<nb, NT, 0, stream>>>(a); ++launch_count();
     }
     const uint32_t ncr = tiles_x - a.fast_itx, nbr = tiles_y - a.fast_ity;
     if (ncr && a.fast_ity) {   // right tile columns of the interior tile rows
         const dim3 nb(ncr, a.fast_ity, a.n_images);
         if (ncr == 1 && a.w == tiles_x * (uint32_t)TW) {
-            hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 4><<<nb, NT, 0, es>>>(a); ++launch_count();
+            hgi_tile_fast_part_kernel<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 4><<<nb, NT, 0, es>>>(a); ++launch_count();
         } else {
-            hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 2><<<nb, NT, 0, es>>>(a); ++launch_count();
+            hgi_tile_fast_part_kernel<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 2><<<nb, NT, 0, es>>>(a); ++launch_count();
         }
     }
     if (nbr) {                 // bottom tile rows
         const dim3 nb(tiles_x, nbr, a.n_images);
-        hgi_tile_fast_part_kernel<MODE, INTERP, false, EXTRA, NLEV, ALIGNED, 3><<<nb, NT, 0, es>>>(a); ++launch_count();
+        hgi_tile_fast_part_kernel<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 3><<<nb, NT, 0, es>>>(a); ++launch_count();
     }
     if (fork) {
         cudaError_t e = cudaEventRecord(a.ev_join, a.side_stream);
@@ -585,17 +585,38 @@ cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
         if (args.c_recon) a.c_recon = args.c_recon + (size_t)first * args.cpitch * args.ch;
         if (args.c_q) a.c_q = args.c_q + (size_t)first * args.cpitch * args.ch;
         const dim3 nb(tiles_x, tiles_y, a.n_images);
+#ifdef HGI_VAR_SPLIT_LIGHT
+        // the light kernels as interior + right-column + bottom-row launches too (headline instantiations only)
+        constexpr bool kSplitLight = ALIGNED && NLEV == 4;
+#else
+        constexpr bool kSplitLight = false;
+#endif
+        const bool big = (uint64_t)tiles_x * tiles_y * a.n_images >= kSplitMinTiles;
         if (MODE == kModeDecode) {
+            if constexpr (kSplitLight && MODE == kModeDecode) {
+                if (big) {
+                    const cudaError_t es = launch_fast_split<kModeDecode, INTERP, true, false, NLEV, ALIGNED>(a, tiles_x, tiles_y, stream);
+                    if (es != cudaSuccess) return es;
+                    continue;
+                }
+            }
             hgi_tile_fast_kernel<kModeDecode, INTERP, true, false, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a); ++launch_count();
         } else {
             const bool extra = (a.recon_out != nullptr);
             const bool ident = (a.quant_error == 0);
+            if constexpr (kSplitLight && MODE == kModeEncode) {
+                if (ident && !extra && big) {
+                    const cudaError_t es = launch_fast_split<kModeEncode, INTERP, true, false, NLEV, ALIGNED>(a, tiles_x, tiles_y, stream);
+                    if (es != cudaSuccess) return es;
+                    continue;
+                }
+            }
             if (ident && !extra) { hgi_tile_fast_kernel<kModeEncode, INTERP, true, false, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
             else if (ident) { hgi_tile_fast_kernel<kModeEncode, INTERP, true, true, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
             else if constexpr (ALIGNED && NLEV == 4 && MODE == kModeEncode) {
                 if ((uint64_t)tiles_x * tiles_y * a.n_images >= kSplitMinTiles) {
-                    const cudaError_t es = extra ? launch_fast_split<kModeEncode, INTERP, true, NLEV, ALIGNED>(a, tiles_x, tiles_y, stream)
-                                                 : launch_fast_split<kModeEncode, INTERP, false, NLEV, ALIGNED>(a, tiles_x, tiles_y, stream);
+                    const cudaError_t es = extra ? launch_fast_split<kModeEncode, INTERP, false, true, NLEV, ALIGNED>(a, tiles_x, tiles_y, stream)
+                                                 : launch_fast_split<kModeEncode, INTERP, false, false, NLEV, ALIGNED>(a, tiles_x, tiles_y, stream);
                     if (es != cudaSuccess) return es;
                 }   // small jobs: one launch, less latency
                 else if (!extra) { hgi_tile_fast_kernel<kModeEncode, INTERP, false, false, NLEV, ALIGNED><<<nb, NT, 0, stream>>>(a); ++launch_count(); }
