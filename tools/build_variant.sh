@@ -9,6 +9,13 @@
 #   -DHGI_FAST_MIN_BLOCKS=n / -DHGI_FAST_MIN_BLOCKS_LIGHT=n   CTAs per SM (quantizing encode / light kernels)
 #   -DHGI_FAST_TILE_H=128 -DHGI_FAST_NT=256                   tile shape / CTA size
 #   -DHGI_VAR_STOP_AFTER=1|2|3   cut after set-up / s=8,4 / s=2 and copy the pixels out (tools/time_encode.py)
+#   -DHGI_VAR_PRED_YB            predictor lanes 2T + 4w + 7 times 1/8 (first fp16 form);  -DHGI_VAR_PRED2_SHIFT  decode predictor as an integer shift
+#   -DHGI_VAR_FULL_FRINGE2       s = 2 fringe as full SWAR words (three points per cell) instead of fringe2_word
+#   -DHGI_VAR_HALO_TWO_WARPS[_DECODE]   halo chunks fetched by whole warps 1 and 2
+#   -DHGI_VAR_STCS / -DHGI_VAR_STCG     streaming / L2-only stores of the output chunks
+#   -DHGI_VAR_SPLIT_LIGHT        decode and the identity encode as interior + edge launches too
+#   -DHGI_VAR_HMUL_MASKS=n, -DHGI_VAR_INTQ, -DHGI_VAR_POISON_SMEM=0xXX   see hgi_tile_swar.cuh / hgi_tile_fast.cu
+# Run-time knobs for tools/ab_bench.py (name=lib.so,ENV=VALUE): HGI_B200_PREFETCH, HGI_B200_SPLIT_MIN
 set -e
 cd "$(dirname "$0")/../rustyhgi_b200/csrc"
 name=$1; shift
