@@ -222,7 +222,11 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     // (2048 frames, same box): spread over the upper half of the CTA, one chunk per thread (decode 1.258 ms, encode
     // Medium 1.681, encode Lossless 1.274), or all on the LAST WARP, NRIGHT/32 + 1 chunks per lane, so that the other
     // warps skip the block with one uniform branch (1.266 / 1.722 / 1.242): the identity encode takes the second.
+#ifdef HGI_VAR_HALO_WARP_DECODE
+    constexpr bool HALO_WARP = ((MODE == kModeEncode) && IDENTITY) || MODE == kModeDecode;
+#else
     constexpr bool HALO_WARP = (MODE == kModeEncode) && IDENTITY;
+#endif
     constexpr int NRIGHT = TH / 2, NHALO = NRIGHT + 27, NRL = NRIGHT / 32;
     // HGI_VAR_HALO_TWO_WARPS / _DECODE: whole warps fetch the halo (warp 1 the right column, warp 2 the bottom rows), A/B
     // hook: encode Medium +1 % slower, decode -0.8 % (inside the noise) -- not the default
@@ -474,7 +478,11 @@ hgi_tile_fast_kernel(const PassArgs p)
     // bodies in one kernel its code is 43 KB and it runs 12 % slower, an instruction-cache effect
     constexpr bool kSplit = ((MODE == kModeDecode) || IDENTITY) && ALIGNED && NLEV == 4;
     if (kSplit) {
+#ifdef HGI_VAR_INTERIOR_BY_SIZE
         const bool interior = (blockIdx.x + 1) * TW + FMAX + 1 <= p.w && (blockIdx.y + 1) * TH + FMAX + 1 <= p.h;
+#else
+        const bool interior = blockIdx.x < p.fast_itx && blockIdx.y < p.fast_ity;   // the launcher's counts of interior tile columns / rows
+#endif
         if (interior) {
             tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 0>(p, sm, blockIdx.x, blockIdx.y);
             return;
@@ -585,6 +593,9 @@ cudaError_t launch_fast_n(const PassArgs& args, cudaStream_t stream)
         if (args.c_recon) a.c_recon = args.c_recon + (size_t)first * args.cpitch * args.ch;
         if (args.c_q) a.c_q = args.c_q + (size_t)first * args.cpitch * args.ch;
         const dim3 nb(tiles_x, tiles_y, a.n_images);
+        // interior tile columns / rows (tile + halo inside the plane), for the bodies without in-image predicates
+        a.fast_itx = a.w >= (uint32_t)(FMAX + 1) ? min(tiles_x, (a.w - (FMAX + 1)) / TW) : 0u;
+        a.fast_ity = a.h >= (uint32_t)(FMAX + 1) ? min(tiles_y, (a.h - (FMAX + 1)) / TH) : 0u;
 #ifdef HGI_VAR_SPLIT_LIGHT
         // the light kernels as interior + right-column + bottom-row launches too (headline instantiations only)
         constexpr bool kSplitLight = ALIGNED && NLEV == 4;
