@@ -21,8 +21,9 @@ def main():
     a = ap.parse_args()
     libs = [l.split("=", 1) for l in a.libs]
     res = {n: [] for n, _ in libs}
-    for _ in range(a.rounds):
-        for name, path in libs:
+    for rnd in range(a.rounds):
+        order = libs[rnd % len(libs):] + libs[:rnd % len(libs)]      # rotate: the first run after a pause sees a cooler, faster GPU
+        for name, path in order:
             path, *extra = path.split(",")
             env = dict(os.environ, HGI_B200_LIB=os.path.abspath(path), **dict(e.split("=", 1) for e in extra))
             out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(a.steps), "--no-cpu", "--no-e2e",
