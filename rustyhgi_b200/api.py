@@ -111,6 +111,10 @@ class Context:
         if rc:
             raise HgiError(rc, "hgi_ctx_set_path")
 
+    def set_pipeline(self, chunk_mb=0, slots=0):
+        """Chunk size (MiB) and stream slots of the host-pointer entry points; 0 = default (hgi_ctx_set_pipeline)."""
+        self.check(_lib.lib().hgi_ctx_set_pipeline(self._h, int(chunk_mb), int(slots)), "hgi_ctx_set_pipeline")
+
     def check(self, rc, where):
         if rc:
             raise HgiError(rc, where, _lib.lib().hgi_ctx_last_cuda_error_string(self._h).decode()

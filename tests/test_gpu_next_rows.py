@@ -134,7 +134,7 @@ def test_host_reductions_in_many_chunks():
     """hgi_histogram_u8 / hgi_error_metrics_u8 / hgi_rgb_to_luma_u8 cut their input into chunks that alternate between
     two pipeline slots; with 1 MB chunks a 5.3 MB input is six of them (odd count, ragged tail)."""
     ctx = hgi.Context()
-    ctx.check(hgi.lib().hgi_ctx_set_pipeline(ctx._h, 1, 0), "hgi_ctx_set_pipeline")
+    ctx.set_pipeline(chunk_mb=1)
     rng = np.random.default_rng(9)
     n = 5 * (1 << 20) + 333_333
     a = rng.integers(0, 256, n).astype(np.uint8)
