@@ -32,7 +32,8 @@ struct PassArgs {
     uint32_t d_log2;         // log2(D)
     uint32_t nlev;           // levels fused in this pass (1..4); coarse step F = 2^nlev
     uint32_t tiles_x, tiles_y;
-    uint32_t fast_tx, fast_itx, fast_ity;   // fast tile kernel, split launch: tiles per row, interior tile columns / rows
+    uint32_t fast_tx, fast_itx, fast_ity;   // fast tile kernel: tiles per row, interior tile columns / rows (tile + halo inside the plane)
+    uint32_t fast_rcol;                     // 1: there is exactly one non-interior tile column and it is a whole tile wide
     uint32_t n_images;
     // fast kernel, quantizing encode, interior tiles: L2 prefetch of the tile at pf_src = src + distance (the same tile of a later
     // plane, or a tile some tile rows further down a large plane) by the CTAs with image index < pf_zlim and tile row

@@ -233,3 +233,21 @@ def test_launch_chains_are_replayed_from_graphs(ctx):
     enc.encode_device(t, grids_out=g2, stream=st.cuda_stream)
     st.synchronize()
     assert (g2.cpu().numpy() == want_g).all()
+
+
+def test_whole_tile_right_column_bodies(ctx):
+    """Planes whose width is a multiple of the tile width (128) have exactly one non-interior tile column: decode and the
+    identity encode run it through a body with constant extents (EDGE = 2) inside the kernel, the quantizing encode as a
+    launch of its own when the job is large.  Heights around the tile-row and halo boundaries (64 k + 0..17), one to
+    three interior tile rows, noise (every fix-up path) and a photograph-like plane."""
+    rng = np.random.default_rng(21)
+    for w in (128, 256, 640):
+        for h in (64, 81, 82, 128 + 17, 128 + 18, 200, 3 * 64 + 1):
+            for q in (0, 2):
+                imgs = np.stack([rng.integers(0, 256, (h, w)).astype(np.uint8), photo_like(w, h, w + h)])
+                want_g = oc.encode_batch(imgs, 4, qlevel=q)
+                want_r = oc.decode_batch(want_g, 4)
+                enc = hgi.Encoder(hgi.Crossed, hgi.Linear(Q(q)), 4, ctx=ctx)
+                grids = enc.encode_batch(imgs)
+                assert (grids == want_g).all(), (w, h, q)
+                assert (hgi.Decoder(hgi.Crossed, ctx=ctx).decode_batch(4, grids) == want_r).all(), (w, h, q)
