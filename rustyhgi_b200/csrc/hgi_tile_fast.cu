@@ -158,6 +158,7 @@ __device__ __forceinline__ FastSmem& opaque_smem(FastSmem& s)
 // EDGE = 0: the tile and its whole halo lie inside the image, so every extent is a compile-time constant
 // EDGE = 2: a tile of the right tile column of a plane whose width is a multiple of the tile width, in a tile row whose
 //           halo rows are inside the image: exactly TW columns (no right halo), all rows -- constants again
+// EDGE = 3: a tile of a bottom tile row whose column (with its right halo) is inside the image: all columns, run-time rows
 // EDGE = 1: anything else
 // and all the in-image predicates (loads, stores, fringe cells, masks) fold away.
 template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED, int EDGE>
@@ -171,7 +172,7 @@ __device__ __forceinline__ void tile_body(const PassArgs& p, FastSmem& sm, uint3
     const uint32_t img = blockIdx.z;
     const uint32_t X0 = tx * TW, Y0 = ty * TH;
     const int xin = EDGE == 1 ? (int)min((uint32_t)(TW + FMAX + 1), p.w - X0) : (EDGE == 2 ? TW : TW + FMAX + 1);   // in-image extent of tile + halo
-    const int yin = EDGE == 1 ? (int)min((uint32_t)(TH + FMAX + 1), p.h - Y0) : TH + FMAX + 1;
+    const int yin = (EDGE == 1 || EDGE == 3) ? (int)min((uint32_t)(TH + FMAX + 1), p.h - Y0) : TH + FMAX + 1;
     const bool edge = EDGE != 0;
     const size_t tile_off = ((size_t)img * p.h + Y0) * p.pitch + X0;   // CTA-uniform; the same in the source and output planes
     const size_t pitch = (size_t)p.pitch;
@@ -493,6 +494,12 @@ hgi_tile_fast_kernel(const PassArgs p)
         // edge body's ~810: -0.7 % per light kernel in power-capped runs, nothing at full clock where they are DRAM-bound)
         if (p.fast_rcol != 0u && blockIdx.x == p.fast_itx && blockIdx.y < p.fast_ity) {
             tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 2>(p, sm, blockIdx.x, blockIdx.y);
+            return;
+        }
+#endif
+#ifdef HGI_VAR_LIGHT_BOTTOM_BODY
+        if (blockIdx.x < p.fast_itx) {   // a bottom tile row under interior tile columns: constant column extents (EDGE = 3)
+            tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 3>(p, sm, blockIdx.x, blockIdx.y);
             return;
         }
 #endif
