@@ -511,7 +511,9 @@ hgi_tile_fast_kernel(const PassArgs p)
 // PART 1 = the interior tiles [0, fast_itx) x [0, fast_ity) with the predicate-free body;
 // PART 2 = the right tile columns [fast_itx, tiles_x) of the interior tile rows, general edge body;
 // PART 4 = the same when there is ONE right column and it is exactly TW wide (width % TW == 0): constants again;
-// PART 3 = the bottom tile rows [fast_ity, tiles_y), all columns, general edge body.
+// PART 3 = the bottom tile rows [fast_ity, tiles_y), all columns, general edge body;
+// PART 5 + 6 (-DHGI_VAR_SPLIT_BOTTOM) = the bottom tile rows as interior columns (constant column extents, EDGE = 3) +
+//          right columns (general edge body).
 template <int MODE, int INTERP, bool IDENTITY, bool EXTRA, int NLEV, bool ALIGNED, int PART>
 __global__ void __launch_bounds__(NT, (IDENTITY && !EXTRA && ALIGNED && NLEV == 4) ? HGI_FAST_MIN_BLOCKS_LIGHT : HGI_FAST_MIN_BLOCKS)
 hgi_tile_fast_part_kernel(const PassArgs p)
@@ -521,6 +523,8 @@ hgi_tile_fast_part_kernel(const PassArgs p)
     if (PART == 1) tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 0>(p, sm, blockIdx.x, blockIdx.y);
     else if (PART == 2) tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 1>(p, sm, p.fast_itx + blockIdx.x, blockIdx.y);
     else if (PART == 4) tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 2>(p, sm, p.fast_itx + blockIdx.x, blockIdx.y);
+    else if (PART == 5) tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 3>(p, sm, blockIdx.x, p.fast_ity + blockIdx.y);
+    else if (PART == 6) tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 1>(p, sm, p.fast_itx + blockIdx.x, p.fast_ity + blockIdx.y);
     else tile_body<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 1>(p, sm, blockIdx.x, p.fast_ity + blockIdx.y);
 }
 
@@ -561,6 +565,13 @@ cudaError_t launch_fast_split(PassArgs& a, uint32_t tiles_x, uint32_t tiles_y, c
             hgi_tile_fast_part_kernel<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 2><<<nb, NT, 0, es>>>(a); ++launch_count();
         }
     }
+#ifdef HGI_VAR_SPLIT_BOTTOM
+    if (nbr && a.fast_itx && ncr) {   // bottom tile rows: interior columns with constant column extents + the right columns
+        const dim3 nb5(a.fast_itx, nbr, a.n_images), nb6(ncr, nbr, a.n_images);
+        hgi_tile_fast_part_kernel<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 5><<<nb5, NT, 0, es>>>(a); ++launch_count();
+        hgi_tile_fast_part_kernel<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 6><<<nb6, NT, 0, es>>>(a); ++launch_count();
+    } else
+#endif
     if (nbr) {                 // bottom tile rows
         const dim3 nb(tiles_x, nbr, a.n_images);
         hgi_tile_fast_part_kernel<MODE, INTERP, IDENTITY, EXTRA, NLEV, ALIGNED, 3><<<nb, NT, 0, es>>>(a); ++launch_count();

@@ -13,7 +13,7 @@
 #   -DHGI_VAR_FULL_FRINGE2       s = 2 fringe as full SWAR words (three points per cell) instead of fringe2_word
 #   -DHGI_VAR_HALO_TWO_WARPS[_DECODE]   halo chunks fetched by whole warps 1 and 2
 #   -DHGI_VAR_STCS / -DHGI_VAR_STCG     streaming / L2-only stores of the output chunks
-#   -DHGI_VAR_SPLIT_LIGHT        decode and the identity encode as interior + edge launches too
+#   -DHGI_VAR_SPLIT_LIGHT        decode and the identity encode as interior + edge launches too;  -DHGI_VAR_SPLIT_BOTTOM  bottom rows of the quantizing encode as two launches
 #   -DHGI_VAR_NO_LIGHT_RIGHT_BODY / -DHGI_VAR_LIGHT_BOTTOM_BODY / -DHGI_VAR_INTERIOR_BY_SIZE / -DHGI_VAR_HALO_WARP_DECODE   bodies and roles of the light kernels
 #   -DHGI_VAR_HMUL_MASKS=n, -DHGI_VAR_INTQ, -DHGI_VAR_POISON_SMEM=0xXX   see hgi_tile_swar.cuh / hgi_tile_fast.cu
 # Run-time knobs for tools/ab_bench.py (name=lib.so,ENV=VALUE): HGI_B200_PREFETCH, HGI_B200_SPLIT_MIN
