@@ -118,6 +118,22 @@ __global__ void k_check(uint32_t K, uint32_t c1, uint32_t S, uint32_t c2, uint32
     if (m != want) atomicAdd(bad + 1, 1u);
 }
 
+// The predictor's divide-and-floor (pred_pk2 / pred2 of hgi_tile_swar.cuh): for every m = T + 2w in 0..1022, in both lanes
+// (lane 1 carries 1022 - m), RN(m b + 512) == 512 + (m+1)/4, RN(256 - m b) == 256 - (m+1)/4 and RN(m b) == (m+1)/4 with
+// b = 1/4 - 2^-13 (0x33FF); and the fix-up mask 0x0100 * 255/256 == 0x00FF.
+__global__ void k_check_pred(uint32_t* bad)
+{
+    const uint32_t m0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m0 > 1022u) return;
+    const uint32_t m1 = 1022u - m0, m = m0 | (m1 << 16);
+    const uint32_t p = hfma2(m, 0x33FF33FFu, 0x02000200u), pk = hfma2(m, 0xB3FFB3FFu, 0x01000100u), pd = hfma2(m, 0x33FF33FFu, 0u);
+    const uint32_t w0 = (m0 + 1u) / 4u, w1 = (m1 + 1u) / 4u;
+    if (p != ((512u + w0) | ((512u + w1) << 16)) || pk != ((256u - w0) | ((256u - w1) << 16)) || pd != (w0 | (w1 << 16))) atomicAdd(bad, 1u);
+    uint32_t x = (m0 & 1u ? 0x0100u : 0u) | (m0 & 2u ? 0x01000000u : 0u), mk;
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(mk) : "r"(x), "r"(0x3BF83BF8u));
+    if (mk != ((m0 & 1u ? 0x00FFu : 0u) | (m0 & 2u ? 0x00FF0000u : 0u))) atomicAdd(bad + 1, 1u);
+}
+
 static uint16_t f2h(double v)   // round-to-nearest-even double -> fp16 bits (normal and subnormal), v finite
 {
     uint16_t best = 0;
@@ -177,6 +193,11 @@ int main()
         printf("fp16 quantizer e=%u: K=%04x c1=%04x S=%04x c2=%04x  mismatching lane pairs: %u   fp16-compare mismatches: %u\n",
                e, K, c1, S, c2, hb[0], hb[1]);
     }
+    cudaMemset(bad, 0, 2 * sizeof(uint32_t));
+    k_check_pred<<<4, 256>>>(bad);
+    uint32_t pb[2];
+    cudaMemcpy(pb, bad, sizeof(pb), cudaMemcpyDeviceToHost);
+    printf("fp16 predictor division by 0x33FF, m = 0..1022 in both lanes: mismatches: %u   fix-up mask mismatches: %u\n", pb[0], pb[1]);
     printf("cuda status: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
